@@ -1,0 +1,152 @@
+"""ctypes front-end of oracle/raster_oracle.c (plain-C restatement of the reference path).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  All arrays are numpy, C-contiguous,
+float32 / int32.  Every function cites the reference lines it restates in raster_oracle.c.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libraster_oracle.so")
+_SRC = os.path.join(_HERE, "raster_oracle.c")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def build(force=False):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        subprocess.check_call(
+            ["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-ffp-contract=off",
+             "-fno-fast-math", "-o", _SO, _SRC, "-lm"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        L.pmr_oracle_forward.argtypes = [_f32p, _i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         _i32p, _f32p, _f32p, _i64p]
+        L.pmr_oracle_forward.restype = None
+        L.pmr_oracle_backward.argtypes = [_f32p, ctypes.c_int64, _f32p, _i32p, _i32p, _f32p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
+        L.pmr_oracle_backward.restype = None
+        L.pmr_oracle_backward_f64acc.argtypes = [_f32p, ctypes.c_int64, _f32p, _i32p, _i32p, _f32p,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p]
+        L.pmr_oracle_backward_f64acc.restype = None
+        L.pmr_oracle_interp_forward.argtypes = [_f32p, _i32p, _i32p, _f32p, _f32p,
+                                                ctypes.c_int, ctypes.c_int64, _f32p]
+        L.pmr_oracle_interp_forward.restype = None
+        L.pmr_oracle_interp_backward.argtypes = [_f32p, _f32p, _i32p, _i32p, _f32p, _f32p,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+                                                 _f32p, _f32p]
+        L.pmr_oracle_interp_backward.restype = None
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def forward(vertices, triangles, image_width, image_height, return_counters=False):
+    """One image.  vertices [V,4], triangles [T,3] -> ids [H,W] i32, bary [H,W,3], z [H,W]."""
+    v, t = _f32(vertices), _i32(triangles)
+    assert v.ndim == 2 and v.shape[1] == 4 and t.ndim == 2 and t.shape[1] == 3
+    W, H = int(image_width), int(image_height)
+    ids = np.empty((H, W), np.int32)
+    bary = np.empty((H, W, 3), np.float32)
+    z = np.empty((H, W), np.float32)
+    counters = np.zeros(3, np.int64)
+    lib().pmr_oracle_forward(_p(v, _f32p), _p(t, _i32p), t.shape[0], W, H,
+                             _p(ids, _i32p), _p(bary, _f32p), _p(z, _f32p), _p(counters, _i64p))
+    if return_counters:
+        return ids, bary, z, counters
+    return ids, bary, z
+
+
+def backward(df_dbary, vertices, triangles, ids, bary):
+    """One image.  -> df_dvertices [V,4] (columns x, y, w; z column zero)."""
+    g, v, t, i, b = _f32(df_dbary), _f32(vertices), _i32(triangles), _i32(ids), _f32(bary)
+    H, W = i.shape
+    out = np.empty((v.shape[0], 4), np.float32)
+    lib().pmr_oracle_backward(_p(g, _f32p), 3, _p(v, _f32p), _p(t, _i32p), _p(i, _i32p),
+                              _p(b, _f32p), v.shape[0], W, H, _p(out, _f32p))
+    return out
+
+
+def backward_f64acc(df_dbary, vertices, triangles, ids, bary):
+    """Same fp32 per-pixel terms summed in double (SURVEY.md F5 yardstick)."""
+    g, v, t, i, b = _f32(df_dbary), _f32(vertices), _i32(triangles), _i32(ids), _f32(bary)
+    H, W = i.shape
+    out = np.empty((v.shape[0], 4), np.float64)
+    lib().pmr_oracle_backward_f64acc(_p(g, _f32p), 3, _p(v, _f32p), _p(t, _i32p), _p(i, _i32p),
+                                     _p(b, _f32p), v.shape[0], W, H, _p(out, _f64p))
+    return out
+
+
+def interp_forward(attributes, triangles, ids, bary, background):
+    """One image.  attributes [V,A] -> out [H,W,A]  (rast.py:118-150)."""
+    a, t, i, b, bg = _f32(attributes), _i32(triangles), _i32(ids), _f32(bary), _f32(background)
+    H, W = i.shape
+    A = a.shape[1]
+    out = np.empty((H, W, A), np.float32)
+    lib().pmr_oracle_interp_forward(_p(a, _f32p), _p(t, _i32p), _p(i, _i32p), _p(b, _f32p),
+                                    _p(bg, _f32p), A, H * W, _p(out, _f32p))
+    return out
+
+
+def interp_backward(grad_out, attributes, triangles, ids, bary, background):
+    """One image.  -> (d_attributes [V,A], d_bary [H,W,3])  (autograd of rast.py:118-150)."""
+    g, a, t = _f32(grad_out), _f32(attributes), _i32(triangles)
+    i, b, bg = _i32(ids), _f32(bary), _f32(background)
+    H, W = i.shape
+    V, A = a.shape
+    dattr = np.empty((V, A), np.float32)
+    dbary = np.empty((H, W, 3), np.float32)
+    lib().pmr_oracle_interp_backward(_p(g, _f32p), _p(a, _f32p), _p(t, _i32p), _p(i, _i32p),
+                                     _p(b, _f32p), _p(bg, _f32p), V, A, H * W,
+                                     _p(dattr, _f32p), _p(dbary, _f32p))
+    return dattr, dbary
+
+
+def rasterize_clip_space(clip_space_vertices, attributes, triangles, image_width, image_height,
+                         background_value, grad_out=None):
+    """Batched restatement of rast.py:66-152 (a Python loop over images, like rast.py:112).
+
+    Returns dict(out, ids, bary, z) and, when grad_out [B,H,W,A] is given, also
+    d_vertices [B,V,4] and d_attributes [B,V,A].
+    """
+    cv, at, tr = _f32(clip_space_vertices), _f32(attributes), _i32(triangles)
+    bg = _f32(np.broadcast_to(np.asarray(background_value, np.float32), (at.shape[2],)))
+    B = cv.shape[0]
+    res = dict(out=[], ids=[], bary=[], z=[])
+    if grad_out is not None:
+        res.update(d_vertices=[], d_attributes=[])
+    for b in range(B):
+        ids, bary, z = forward(cv[b], tr, image_width, image_height)
+        res["ids"].append(ids)
+        res["bary"].append(bary)
+        res["z"].append(z)
+        res["out"].append(interp_forward(at[b], tr, ids, bary, bg))
+        if grad_out is not None:
+            dattr, dbary = interp_backward(grad_out[b], at[b], tr, ids, bary, bg)
+            res["d_attributes"].append(dattr)
+            res["d_vertices"].append(backward(dbary, cv[b], tr, ids, bary))
+    return {k: np.stack(v) for k, v in res.items()}
