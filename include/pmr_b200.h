@@ -1,0 +1,142 @@
+/*
+ * pmr_b200.h -- C ABI of libpmr_b200.so, the sm_100a implementation of pytorch_mesh_renderer's
+ * barycentric rasterization hot path.
+ *
+ * This is the drop-in boundary.  The reference crosses exactly one language boundary on this
+ * path: Python -> `rasterize_triangles_cpp.forward / .backward`
+ *   (/root/reference/src/mesh_renderer/kernels/rasterize_triangles.cpp:302-307, :131-137,
+ *    exported at :421-424; called from rasterize_triangles_ext.py:39 and :56),
+ * and then interpolates attributes with torch ops in rasterize.py:118-150.  The entry points
+ * below are what a binding for that path binds: plain pointers and sizes, no torch types.
+ * They are batched over images (the reference loops `for b in range(batch_size)` in Python,
+ * rasterize.py:112); B = 1 is the reference's unbatched call.
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers on the context's device unless the function name
+ *     ends in `_host`, in which case they are host pointers and the call copies in and out.
+ *   - Layouts are the reference's, row-major and densely packed:
+ *       vertices   float32 [B, V, 4]   clip-space x y z w          (K.cpp:279-284)
+ *       triangles  int32   [T, 3]      shared by all images        (K.cpp:285-287)
+ *       ids        int32   [B, H, W]   0 also means "no triangle"  (K.cpp:290-294)
+ *       bary       float32 [B, H, W, 3]  (0,0,0) where empty       (K.cpp:295-298)
+ *       z          float32 [B, H, W]     1.0 where empty           (K.cpp:299-301)
+ *       attributes float32 [B, V, A];  image float32 [B, H, W, A]  (rasterize.py:70-95)
+ *     Row iy = 0 is NDC y = -1.  Argument order is (width, height) like the reference's.
+ *   - `vertices` must be 16-byte aligned.  Vertex indices are not range-checked (neither does the
+ *     reference, K.cpp:331-337).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Kernels are
+ *     enqueued on it; only the forward pass of a binned mesh synchronises it once (8-byte
+ *     read-back of the tile-list length).  A context must not be used from two streams at once.
+ *   - Every function returns PMR_OK (0) or a negative PMR_ERR_* code; pmr_last_error() gives the
+ *     message.  There is no CPU fallback: without a CUDA device pmr_create fails.
+ *   - Outputs are fully written by the callee (no pre-initialisation required).
+ */
+#ifndef PMR_B200_H_
+#define PMR_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PMR_API __attribute__((visibility("default")))
+#else
+#define PMR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMR_OK 0
+#define PMR_ERR_INVALID (-1) /* bad argument: NULL pointer, non-positive size, misalignment */
+#define PMR_ERR_CUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define PMR_ERR_SIZE (-3)    /* problem too large for 32-bit tile bookkeeping */
+#define PMR_ERR_NO_DEVICE (-4)
+
+/* Backward accumulation modes. */
+#define PMR_BACKWARD_ATOMIC 0  /* throughput mode: warp-aggregated atomics, fp32 sums in arbitrary order */
+#define PMR_BACKWARD_ORDERED 1 /* parity mode: every vertex component is summed sequentially in ascending
+                                  pixel order, corner 0..2 within a pixel -- the reference's order
+                                  (K.cpp:156-157, 232-269), bit-reproducible */
+
+typedef struct pmr_context pmr_context;
+
+PMR_API int pmr_version(void);
+
+/* Creates a context (workspace + pinned mailbox) on CUDA device `device`. */
+PMR_API int pmr_create(int device, pmr_context **out);
+PMR_API void pmr_destroy(pmr_context *ctx);
+PMR_API const char *pmr_last_error(const pmr_context *ctx);
+
+/* Number of kernels launched through this context so far (bench.py's gpu_launches). */
+PMR_API long long pmr_launch_count(const pmr_context *ctx);
+/* Tile-list entries produced by the last binned forward pass (diagnostics). */
+PMR_API unsigned long long pmr_last_bin_entries(const pmr_context *ctx);
+/* Meshes with at most this many triangles skip the binning pass (default 64). */
+PMR_API int pmr_set_small_mesh_threshold(pmr_context *ctx, int triangles);
+
+/*
+ * rasterize_triangles forward.  Replaces rasterize_triangles_cpp.forward
+ * (rasterize_triangles.cpp:302-419) for B images at once.
+ */
+PMR_API int pmr_rasterize_forward(pmr_context *ctx, const float *vertices, const int32_t *triangles,
+                          int B, int V, int T, int image_width, int image_height,
+                          int32_t *ids, float *bary, float *z, void *stream);
+
+/*
+ * rasterize_triangles backward.  Replaces rasterize_triangles_cpp.backward
+ * (rasterize_triangles.cpp:131-273): df_dbary [B,H,W,3] -> df_dvertices [B,V,4]
+ * (columns x, y, w; the z column is written as zero).
+ */
+PMR_API int pmr_rasterize_backward(pmr_context *ctx, const float *df_dbary, const float *vertices,
+                           const int32_t *triangles, const int32_t *ids, const float *bary,
+                           int B, int V, int T, int image_width, int image_height,
+                           float *df_dvertices, int mode, void *stream);
+
+/*
+ * Attribute interpolation from existing raster buffers.  Replaces the torch-op chain of
+ * rasterize_clip_space (rasterize.py:118-150): gather corner attributes, weight by barycentrics,
+ * alpha = clamp(2*sum(b), 0, 1), blend with `background` [A].
+ */
+PMR_API int pmr_interpolate_forward(pmr_context *ctx, const float *attributes, const int32_t *triangles,
+                            const int32_t *ids, const float *bary, const float *background,
+                            int B, int V, int T, int A, int image_width, int image_height,
+                            float *image, void *stream);
+
+/*
+ * Fused rasterize + interpolate: rasterize_clip_space (rasterize.py:66-152) in one pass.  Also
+ * returns the raster buffers the backward pass needs.
+ */
+PMR_API int pmr_rasterize_interpolate_forward(pmr_context *ctx, const float *vertices, const float *attributes,
+                                      const int32_t *triangles, const float *background,
+                                      int B, int V, int T, int A, int image_width, int image_height,
+                                      int32_t *ids, float *bary, float *z, float *image, void *stream);
+
+/*
+ * Backward of rasterize_clip_space: grad_image [B,H,W,A] -> d_vertices [B,V,4] and
+ * d_attributes [B,V,A] in one pass (the reference runs autograd through rasterize.py:130-150 and
+ * then rasterize_triangles.cpp:131-273).  Either output may be NULL to skip it.
+ */
+PMR_API int pmr_rasterize_interpolate_backward(pmr_context *ctx, const float *grad_image, const float *vertices,
+                                       const float *attributes, const int32_t *triangles,
+                                       const int32_t *ids, const float *bary,
+                                       int B, int V, int T, int A, int image_width, int image_height,
+                                       float *d_vertices, float *d_attributes, int mode, void *stream);
+
+/*
+ * Host-buffer round trip of rasterize_clip_space forward + backward: copies vertices, attributes,
+ * triangles, background and grad_image to the device, runs the fused forward and backward, copies
+ * image, d_vertices and d_attributes (and, when non-NULL, ids / bary / z) back.  This is the call
+ * bench.py times for `e2e`.  All pointers are HOST pointers (pinned memory makes the copies
+ * asynchronous); the call returns after the results are in host memory.
+ */
+PMR_API int pmr_rasterize_clip_space_host(pmr_context *ctx, const float *vertices, const float *attributes,
+                                  const int32_t *triangles, const float *background,
+                                  const float *grad_image,
+                                  int B, int V, int T, int A, int image_width, int image_height,
+                                  float *image, float *d_vertices, float *d_attributes,
+                                  int32_t *ids, float *bary, float *z, int mode, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMR_B200_H_ */

@@ -1,0 +1,36 @@
+"""Compiles csrc/*.cu into pytorch_mesh_renderer_b200/libpmr_b200.so for sm_100a (nvcc
+cross-compiles without a GPU).  The flags are the ones in csrc/Makefile; -fmad=false,
+-prec-div=true and -ftz=false are part of the numerical contract."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libpmr_b200.so")
+SOURCES = ["c_api.cu", "raster_forward.cu", "raster_backward.cu"]
+HEADERS = ["pmr_internal.cuh", "raster_math.cuh", os.path.join("..", "..", "include", "pmr_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+              "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-extended-lambda"]
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    built = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > built for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not is_stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-shared", "-o", LIB, *SOURCES, "-lcudart"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

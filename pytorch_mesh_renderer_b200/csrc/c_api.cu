@@ -1,0 +1,244 @@
+// c_api.cu -- extern "C" surface of libpmr_b200.so (include/pmr_b200.h): context management,
+// argument validation and the host-buffer round trip.  Kernels live in raster_forward.cu and
+// raster_backward.cu.
+#include <stdarg.h>
+
+#include <new>
+
+#include "pmr_internal.cuh"
+
+struct pmr_context : public pmr::Context {};
+
+namespace pmr {
+
+int set_error(Context *ctx, int code, const char *fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->error, sizeof(ctx->error), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+int check_launch(Context *ctx, const char *what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(ctx, PMR_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  return PMR_OK;
+}
+
+int Buffer::reserve(Context *ctx, size_t need) {
+  if (need <= bytes) return PMR_OK;
+  // Grow geometrically; the old block may still be in use by enqueued work of this context's
+  // stream, and cudaFree synchronises the device before releasing it.
+  size_t want = bytes + bytes / 2;
+  if (want < need) want = need;
+  want = (want + 255) & ~(size_t)255;
+  if (ptr) {
+    cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  const cudaError_t e = cudaMalloc(&ptr, want);
+  if (e != cudaSuccess) {
+    ptr = nullptr;
+    return set_error(ctx, PMR_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+  }
+  bytes = want;
+  return PMR_OK;
+}
+
+void Buffer::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  bytes = 0;
+}
+
+static int validate_common(Context *ctx, int B, int V, int T, int W, int H) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (B < 0 || V < 0 || T < 0) return set_error(ctx, PMR_ERR_INVALID, "negative batch/vertex/triangle count");
+  // rasterize.py:98-101 raises ValueError for non-positive sizes.
+  if (W <= 0) return set_error(ctx, PMR_ERR_INVALID, "Image width must be > 0.");
+  if (H <= 0) return set_error(ctx, PMR_ERR_INVALID, "Image height must be > 0.");
+  if (W > 32768 || H > 32768) return set_error(ctx, PMR_ERR_SIZE, "image larger than 32768 pixels on a side");
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  return PMR_OK;
+}
+
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+}  // namespace pmr
+
+using pmr::Context;
+using pmr::set_error;
+
+extern "C" {
+
+int pmr_version(void) { return 100; }
+
+int pmr_create(int device, pmr_context **out) {
+  if (!out) return PMR_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return PMR_ERR_NO_DEVICE;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return PMR_ERR_CUDA;
+  pmr_context *ctx = new (std::nothrow) pmr_context();
+  if (!ctx) return PMR_ERR_INVALID;
+  ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (cudaMallocHost((void **)&ctx->mailbox, 64) != cudaSuccess) {
+    delete ctx;
+    return PMR_ERR_CUDA;
+  }
+  *out = ctx;
+  return PMR_OK;
+}
+
+void pmr_destroy(pmr_context *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  ctx->bins.release();
+  ctx->lists.release();
+  ctx->scratch.release();
+  if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+  delete ctx;
+}
+
+const char *pmr_last_error(const pmr_context *ctx) { return ctx ? ctx->error : "null context"; }
+long long pmr_launch_count(const pmr_context *ctx) { return ctx ? ctx->launches : 0; }
+unsigned long long pmr_last_bin_entries(const pmr_context *ctx) { return ctx ? ctx->last_bin_entries : 0; }
+
+int pmr_set_small_mesh_threshold(pmr_context *ctx, int triangles) {
+  if (!ctx || triangles < 0) return PMR_ERR_INVALID;
+  ctx->small_mesh_threshold = triangles;
+  return PMR_OK;
+}
+
+int pmr_rasterize_forward(pmr_context *ctx, const float *vertices, const int32_t *triangles, int B, int V,
+                          int T, int W, int H, int32_t *ids, float *bary, float *z, void *stream) {
+  int rc = pmr::validate_common(ctx, B, V, T, W, H);
+  if (rc) return rc;
+  if (B == 0) return PMR_OK;
+  if (!ids || !bary || !z || (T > 0 && (!vertices || !triangles)))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(vertices)) return set_error(ctx, PMR_ERR_INVALID, "vertices must be 16-byte aligned");
+  return pmr::forward_impl(ctx, vertices, triangles, B, V, T, W, H, ids, bary, z, nullptr, nullptr, 0, nullptr,
+                           (cudaStream_t)stream);
+}
+
+int pmr_rasterize_backward(pmr_context *ctx, const float *df_dbary, const float *vertices,
+                           const int32_t *triangles, const int32_t *ids, const float *bary, int B, int V, int T,
+                           int W, int H, float *df_dvertices, int mode, void *stream) {
+  int rc = pmr::validate_common(ctx, B, V, T, W, H);
+  if (rc) return rc;
+  if (B == 0 || V == 0) return PMR_OK;
+  if (!df_dbary || !vertices || !ids || !bary || !df_dvertices || (T > 0 && !triangles))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(vertices)) return set_error(ctx, PMR_ERR_INVALID, "vertices must be 16-byte aligned");
+  return pmr::backward_impl(ctx, df_dbary, nullptr, vertices, nullptr, triangles, ids, bary, B, V, T, 0, W, H,
+                            df_dvertices, nullptr, mode, (cudaStream_t)stream);
+}
+
+int pmr_interpolate_forward(pmr_context *ctx, const float *attributes, const int32_t *triangles,
+                            const int32_t *ids, const float *bary, const float *background, int B, int V, int T,
+                            int A, int W, int H, float *image, void *stream) {
+  int rc = pmr::validate_common(ctx, B, V, T, W, H);
+  if (rc) return rc;
+  if (A < 0) return set_error(ctx, PMR_ERR_INVALID, "negative attribute count");
+  if (B == 0 || A == 0) return PMR_OK;
+  if (!attributes || !triangles || !ids || !bary || !background || !image)
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (T == 0) return set_error(ctx, PMR_ERR_INVALID, "interpolation needs at least one triangle");
+  return pmr::interpolate_impl(ctx, attributes, triangles, ids, bary, background, B, V, A, W, H, image,
+                               (cudaStream_t)stream);
+}
+
+int pmr_rasterize_interpolate_forward(pmr_context *ctx, const float *vertices, const float *attributes,
+                                      const int32_t *triangles, const float *background, int B, int V, int T,
+                                      int A, int W, int H, int32_t *ids, float *bary, float *z, float *image,
+                                      void *stream) {
+  int rc = pmr::validate_common(ctx, B, V, T, W, H);
+  if (rc) return rc;
+  if (A <= 0) return set_error(ctx, PMR_ERR_INVALID, "attribute count must be > 0");
+  if (B == 0) return PMR_OK;
+  if (!ids || !bary || !z || !image || !background || (T > 0 && (!vertices || !triangles || !attributes)))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(vertices)) return set_error(ctx, PMR_ERR_INVALID, "vertices must be 16-byte aligned");
+  return pmr::forward_impl(ctx, vertices, triangles, B, V, T, W, H, ids, bary, z, attributes, background, A,
+                           image, (cudaStream_t)stream);
+}
+
+int pmr_rasterize_interpolate_backward(pmr_context *ctx, const float *grad_image, const float *vertices,
+                                       const float *attributes, const int32_t *triangles, const int32_t *ids,
+                                       const float *bary, int B, int V, int T, int A, int W, int H,
+                                       float *d_vertices, float *d_attributes, int mode, void *stream) {
+  int rc = pmr::validate_common(ctx, B, V, T, W, H);
+  if (rc) return rc;
+  if (A <= 0) return set_error(ctx, PMR_ERR_INVALID, "attribute count must be > 0");
+  if (B == 0 || V == 0) return PMR_OK;
+  if (!grad_image || !vertices || !attributes || !ids || !bary || (T > 0 && !triangles))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(vertices)) return set_error(ctx, PMR_ERR_INVALID, "vertices must be 16-byte aligned");
+  return pmr::backward_impl(ctx, nullptr, grad_image, vertices, attributes, triangles, ids, bary, B, V, T, A, W,
+                            H, d_vertices, d_attributes, mode, (cudaStream_t)stream);
+}
+
+int pmr_rasterize_clip_space_host(pmr_context *ctx, const float *vertices, const float *attributes,
+                                  const int32_t *triangles, const float *background, const float *grad_image,
+                                  int B, int V, int T, int A, int W, int H, float *image, float *d_vertices,
+                                  float *d_attributes, int32_t *ids, float *bary, float *z, int mode,
+                                  void *stream_) {
+  int rc = pmr::validate_common(ctx, B, V, T, W, H);
+  if (rc) return rc;
+  if (A <= 0) return set_error(ctx, PMR_ERR_INVALID, "attribute count must be > 0");
+  if (B == 0) return PMR_OK;
+  if (!vertices || !attributes || !background || !image || (T > 0 && !triangles))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t P = (size_t)B * H * W;
+  const size_t n_v = (size_t)B * V * 4 * sizeof(float), n_a = (size_t)B * V * A * sizeof(float);
+  const size_t n_t = (size_t)T * 3 * sizeof(int32_t), n_bg = (size_t)A * sizeof(float);
+  const size_t n_img = P * A * sizeof(float), n_ids = P * sizeof(int32_t), n_bary = P * 3 * sizeof(float);
+  auto up = [](size_t n) { return (n + 255) & ~(size_t)255; };
+  const bool bwd = grad_image != nullptr;
+  const size_t need = up(n_v) + up(n_a) + up(n_t) + up(n_bg) + up(n_img) * (bwd ? 2 : 1) + up(n_ids) +
+                      up(n_bary) + up(n_ids) + (bwd ? up(n_v) + up(n_a) : 0) + 256;
+  static thread_local pmr::Buffer staging;   // device staging area of the host entry point
+  rc = staging.reserve(ctx, need);
+  if (rc) return rc;
+  char *cur = (char *)staging.ptr;
+  auto take = [&](size_t n) { char *p = cur; cur += up(n); return p; };
+  float *d_v = (float *)take(n_v), *d_a = (float *)take(n_a);
+  int32_t *d_t = (int32_t *)take(n_t);
+  float *d_bg = (float *)take(n_bg), *d_img = (float *)take(n_img);
+  int32_t *d_ids = (int32_t *)take(n_ids);
+  float *d_bary = (float *)take(n_bary), *d_z = (float *)take(n_ids);
+  float *d_g = bwd ? (float *)take(n_img) : nullptr;
+  float *d_dv = bwd ? (float *)take(n_v) : nullptr, *d_da = bwd ? (float *)take(n_a) : nullptr;
+
+  PMR_CUDA(ctx, cudaMemcpyAsync(d_v, vertices, n_v, cudaMemcpyHostToDevice, stream));
+  PMR_CUDA(ctx, cudaMemcpyAsync(d_a, attributes, n_a, cudaMemcpyHostToDevice, stream));
+  if (n_t) PMR_CUDA(ctx, cudaMemcpyAsync(d_t, triangles, n_t, cudaMemcpyHostToDevice, stream));
+  PMR_CUDA(ctx, cudaMemcpyAsync(d_bg, background, n_bg, cudaMemcpyHostToDevice, stream));
+  if (bwd) PMR_CUDA(ctx, cudaMemcpyAsync(d_g, grad_image, n_img, cudaMemcpyHostToDevice, stream));
+  rc = pmr::forward_impl(ctx, d_v, d_t, B, V, T, W, H, d_ids, d_bary, d_z, d_a, d_bg, A, d_img, stream);
+  if (rc) return rc;
+  PMR_CUDA(ctx, cudaMemcpyAsync(image, d_img, n_img, cudaMemcpyDeviceToHost, stream));
+  if (ids) PMR_CUDA(ctx, cudaMemcpyAsync(ids, d_ids, n_ids, cudaMemcpyDeviceToHost, stream));
+  if (bary) PMR_CUDA(ctx, cudaMemcpyAsync(bary, d_bary, n_bary, cudaMemcpyDeviceToHost, stream));
+  if (z) PMR_CUDA(ctx, cudaMemcpyAsync(z, d_z, n_ids, cudaMemcpyDeviceToHost, stream));
+  if (bwd) {
+    rc = pmr::backward_impl(ctx, nullptr, d_g, d_v, d_a, d_t, d_ids, d_bary, B, V, T, A, W, H,
+                            d_vertices ? d_dv : nullptr, d_attributes ? d_da : nullptr, mode, stream);
+    if (rc) return rc;
+    if (d_vertices) PMR_CUDA(ctx, cudaMemcpyAsync(d_vertices, d_dv, n_v, cudaMemcpyDeviceToHost, stream));
+    if (d_attributes) PMR_CUDA(ctx, cudaMemcpyAsync(d_attributes, d_da, n_a, cudaMemcpyDeviceToHost, stream));
+  }
+  PMR_CUDA(ctx, cudaStreamSynchronize(stream));
+  return PMR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// pmr_internal.cuh -- context, workspace and error plumbing shared by the translation units
+// behind include/pmr_b200.h.  No torch types anywhere: the library is plain CUDA runtime.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pmr_b200.h"
+
+namespace pmr {
+
+// Screen tile of the binning pass and of one raster CTA: 16x16 pixels = 8 warps x (8x4) pixels.
+constexpr int kTileW = 16, kTileH = 16, kTileShiftX = 4, kTileShiftY = 4;
+
+struct Context;
+int set_error(Context *ctx, int code, const char *fmt, ...);
+
+// Grow-only device buffer owned by a context (stream-ordered use: one context serves one stream
+// at a time, like the single-threaded reference entry points it replaces).
+struct Buffer {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(Context *ctx, size_t need);
+  void release();
+};
+
+struct Context {
+  int device = 0;
+  int sm_count = 148;
+  int small_mesh_threshold = 64;      // T at or below this: no binning, every tile walks all triangles
+  Buffer bins, lists, scratch;
+  unsigned long long *mailbox = nullptr;   // pinned host word for the tile-list length
+  unsigned long long last_bin_entries = 0;
+  long long launches = 0;             // kernels launched through this context (bench gpu_launches)
+  char error[512] = {0};
+};
+
+int check_launch(Context *ctx, const char *what);
+
+#define PMR_CUDA(ctx, call)                                                                   \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return ::pmr::set_error((ctx), PMR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+// raster_forward.cu
+int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, int V, int T, int W, int H,
+                 int32_t *ids, float *bary, float *z, const float *attrs, const float *bg, int A,
+                 float *image, cudaStream_t stream);
+int interpolate_impl(Context *ctx, const float *attrs, const int32_t *tris, const int32_t *ids,
+                     const float *bary, const float *bg, int B, int V, int A, int W, int H, float *out,
+                     cudaStream_t stream);
+// raster_backward.cu
+int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, const float *verts,
+                  const float *attrs, const int32_t *tris, const int32_t *ids, const float *bary,
+                  int B, int V, int T, int A, int W, int H, float *d_verts, float *d_attrs, int mode,
+                  cudaStream_t stream);
+
+}  // namespace pmr

@@ -1,0 +1,354 @@
+// raster_backward.cu -- backward of rasterize_triangles (K.cpp:131-273) batched over images,
+// optionally fused with the backward of the attribute interpolation (autograd of
+// rast.py:118-150), in two accumulation modes:
+//
+//   PMR_BACKWARD_ATOMIC   one thread per pixel; a warp whose covered pixels all belong to one
+//                         triangle reduces its 9 (+3A) sums with shuffles and issues one set of
+//                         atomics, otherwise lanes scatter individually.  fp32 sums in arbitrary
+//                         order.
+//   PMR_BACKWARD_ORDERED  one warp per (image, vertex): walks the union of the pixel boxes of the
+//                         vertex's triangles in ascending pixel order, lanes evaluate the
+//                         per-pixel terms in parallel and the sums are then folded strictly in
+//                         pixel order, corner 0..2 within a pixel -- the reference's summation
+//                         order (K.cpp:156-157, :232-269; index_put_ order of rast.py:130-132),
+//                         so the result is bit-reproducible and equals the reference's.
+//
+// Per-pixel arithmetic is shared with the forward pass (raster_math.cuh) and follows the
+// reference op for op; compile with -fmad=false.
+#include "pmr_internal.cuh"
+#include "raster_math.cuh"
+
+namespace pmr {
+
+// Everything the backward pass needs to know about one covered pixel.
+struct PixelGrad {
+  int vid[3];        // vertex ids of the pixel's triangle
+  float terms[9];    // vertex_terms(): [3*corner + component]
+  float b[3];
+  float alpha;
+};
+
+// Loads the pixel's triangle, derives d(loss)/d(bary) (given directly, or from the image gradient
+// through the interpolation), and evaluates the nine vertex terms.
+//   fused:  d_img_a = g_a * alpha;  d_b_k = sum_a d_img_a * corner_k[a]  (torch order).
+template <bool FUSED>
+__device__ __forceinline__ void pixel_grad(const float *__restrict__ verts_b, const float *__restrict__ attrs_b,
+                                           const int32_t *__restrict__ tris, int id, const float *bary_p,
+                                           const float *g_p, int A, PixelGrad &out) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) out.vid[j] = __ldg(tris + 3 * (size_t)id + j);
+  const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
+  const float4 p0 = __ldg(v4 + out.vid[0]), p1 = __ldg(v4 + out.vid[1]), p2 = __ldg(v4 + out.vid[2]);
+  out.b[0] = bary_p[0]; out.b[1] = bary_p[1]; out.b[2] = bary_p[2];
+  float g[3];
+  if (FUSED) {
+    const float s = 2.0f * out.b[0] + 2.0f * out.b[1] + 2.0f * out.b[2];
+    out.alpha = fminf(fmaxf(s, 0.0f), 1.0f);
+    const float alpha = out.alpha;
+    const float *c[3] = {attrs_b + (size_t)out.vid[0] * A, attrs_b + (size_t)out.vid[1] * A,
+                         attrs_b + (size_t)out.vid[2] * A};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float *ck = c[k];
+      g[k] = torch_inner_sum(A, [&](int a) { return (g_p[a] * alpha) * __ldg(ck + a); });
+    }
+    // Covered pixels have s ~ 2: the clamp of rast.py:145-146 is saturated and passes no gradient,
+    // so the 2*d_alpha term of the reference's autograd is exactly zero here.
+  } else {
+    out.alpha = 1.0f;
+    g[0] = g_p[0]; g[1] = g_p[1]; g[2] = g_p[2];
+  }
+  float m[9];
+  const float det = adjugate_signed(p0.x, p1.x, p2.x, p0.y, p1.y, p2.y, p0.w, p1.w, p2.w, m);
+  vertex_terms(m, fabsf(det), out.b, g, out.terms);
+}
+
+__device__ __forceinline__ bool pixel_is_covered(int id, const float *bary_p) {
+  // K.cpp:162
+  return !(id == 0 && bary_p[0] + bary_p[1] + bary_p[2] < kDegenerateBarySum);
+}
+
+// x, y, w gradients land in columns 0, 1, 3 of [V,4] (K.cpp:232-269).
+__device__ __forceinline__ int column_of(int c) { return c == 2 ? 3 : c; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Atomic mode
+// ---------------------------------------------------------------------------------------------
+
+template <bool FUSED, int A_STATIC>
+__global__ void __launch_bounds__(256)
+backward_atomic_kernel(const float *__restrict__ grad, const float *__restrict__ verts,
+                       const float *__restrict__ attrs, const int32_t *__restrict__ tris,
+                       const int32_t *__restrict__ ids, const float *__restrict__ bary,
+                       int V, int A_dyn, long long pixels_per_image, long long total_pixels,
+                       float *__restrict__ d_verts, float *__restrict__ d_attrs) {
+  const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool in_range = p < total_pixels;
+  int id = -1;
+  float bp[3] = {0.0f, 0.0f, 0.0f};
+  if (in_range) {
+    id = ids[p];
+    bp[0] = bary[3 * p]; bp[1] = bary[3 * p + 1]; bp[2] = bary[3 * p + 2];
+    if (!pixel_is_covered(id, bp)) id = -1;
+  }
+  const unsigned covered = __ballot_sync(0xffffffffu, id >= 0);
+  if (covered == 0u) return;
+  // All 32 pixels of a warp lie in one image only if the row stride allows; key on (image, id).
+  const int b = in_range ? (int)(p / pixels_per_image) : 0;
+  const long long key = id >= 0 ? ((long long)b << 32) | (unsigned)id : -1;
+  const int leader = __ffs(covered) - 1;
+  const long long leader_key = __shfl_sync(0xffffffffu, key, leader);
+  const bool uniform = __all_sync(0xffffffffu, key == leader_key || key < 0);
+
+  PixelGrad pg;
+  const float *g_p = nullptr;
+  if (id >= 0) {
+    const float *verts_b = verts + (size_t)b * V * 4;
+    const float *attrs_b = FUSED ? attrs + (size_t)b * V * A : nullptr;
+    g_p = grad + (size_t)p * (FUSED ? A : 3);
+    pixel_grad<FUSED>(verts_b, attrs_b, tris, id, bp, g_p, A, pg);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) pg.terms[k] = 0.0f;
+    pg.b[0] = pg.b[1] = pg.b[2] = 0.0f; pg.alpha = 0.0f;
+    pg.vid[0] = pg.vid[1] = pg.vid[2] = 0;
+  }
+
+  if (uniform) {
+    // One triangle for the whole warp: reduce, then one lane per value issues the atomic.
+    const int v0 = __shfl_sync(0xffffffffu, pg.vid[0], leader);
+    const int v1 = __shfl_sync(0xffffffffu, pg.vid[1], leader);
+    const int v2 = __shfl_sync(0xffffffffu, pg.vid[2], leader);
+    const int lb = __shfl_sync(0xffffffffu, b, leader);
+    const int vv[3] = {v0, v1, v2};
+    if (d_verts != nullptr) {
+      float *dv = d_verts + (size_t)lb * V * 4;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float s = warp_sum(pg.terms[k]);
+        if (lane == k) atomicAdd(dv + (size_t)vv[k / 3] * 4 + column_of(k % 3), s);
+      }
+    }
+    if (FUSED && d_attrs != nullptr) {
+      float *da = d_attrs + (size_t)lb * V * A;
+      for (int a = 0; a < A; ++a) {
+        const float d_img = id >= 0 ? g_p[a] * pg.alpha : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float s = warp_sum(d_img * pg.b[k]);
+          if (lane == ((3 * a + k) & 31)) atomicAdd(da + (size_t)vv[k] * A + a, s);
+        }
+      }
+    }
+    return;
+  }
+  if (id < 0) return;
+  if (d_verts != nullptr) {
+    float *dv = d_verts + (size_t)b * V * 4;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) atomicAdd(dv + (size_t)pg.vid[k / 3] * 4 + column_of(k % 3), pg.terms[k]);
+  }
+  if (FUSED && d_attrs != nullptr) {
+    float *da = d_attrs + (size_t)b * V * A;
+    for (int a = 0; a < A; ++a) {
+      const float d_img = g_p[a] * pg.alpha;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) atomicAdd(da + (size_t)pg.vid[k] * A + a, d_img * pg.b[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ordered (parity) mode
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+vertex_box_init_kernel(int4 *__restrict__ vbox, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) vbox[i] = make_int4(INT_MAX, INT_MIN, INT_MAX, INT_MIN);   // left right bottom top
+}
+
+// Union, per (image, vertex), of the pixel boxes of the triangles that use the vertex.  A pixel
+// drawn from triangle t always lies inside t's box (K.cpp:374-375), so the union bounds every
+// pixel that can contribute to the vertex.
+__global__ void __launch_bounds__(256)
+vertex_box_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int T,
+                  int W, int H, float half_w, float half_h, int4 *__restrict__ vbox) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int i0 = __ldg(tris + 3 * (size_t)t), i1 = __ldg(tris + 3 * (size_t)t + 1), i2 = __ldg(tris + 3 * (size_t)t + 2);
+  const float4 *v4 = reinterpret_cast<const float4 *>(verts + (size_t)b * V * 4);
+  const PixelBox bx = triangle_box(__ldg(v4 + i0), __ldg(v4 + i1), __ldg(v4 + i2), half_w, half_h, W, H);
+  if (bx.left >= bx.right || bx.bottom >= bx.top) return;
+  const int vid[3] = {i0, i1, i2};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    int *q = reinterpret_cast<int *>(vbox + (size_t)b * V + vid[j]);
+    atomicMin(q + 0, bx.left);
+    atomicMax(q + 1, bx.right);
+    atomicMin(q + 2, bx.bottom);
+    atomicMax(q + 3, bx.top);
+  }
+}
+
+constexpr int kOrderedWarps = 8;
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kOrderedWarps * 32)
+backward_ordered_kernel(const float *__restrict__ grad, const float *__restrict__ verts,
+                        const float *__restrict__ attrs, const int32_t *__restrict__ tris,
+                        const int32_t *__restrict__ ids, const float *__restrict__ bary,
+                        const int4 *__restrict__ vbox, int V, int A, int W, int H, long long n_pairs,
+                        float *__restrict__ d_verts, float *__restrict__ d_attrs) {
+  extern __shared__ float rows_all[];   // [warp][lane][corner][3 + A]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pair = (long long)blockIdx.x * kOrderedWarps + warp;
+  if (pair >= n_pairs) return;
+  const int b = (int)(pair / V), v = (int)(pair % V);
+  const int ncomp = 3 + (FUSED ? A : 0);
+  float *rows = rows_all + (size_t)warp * 32 * 3 * ncomp;
+  const int4 box = vbox[pair];
+  const float *verts_b = verts + (size_t)b * V * 4;
+  const float *attrs_b = FUSED ? attrs + (size_t)b * V * A : nullptr;
+
+  constexpr int kMaxSlots = 4;          // components lane, lane+32, ... (A <= 125)
+  float acc[kMaxSlots] = {0.0f, 0.0f, 0.0f, 0.0f};
+
+  const int bw = box.y - box.x;
+  const long long n = (box.x < box.y && box.z < box.w) ? (long long)bw * (box.w - box.z) : 0;
+  for (long long k0 = 0; k0 < n; k0 += 32) {
+    const long long k = k0 + lane;
+    int id = -1, corners = 0;
+    long long p = 0;
+    float bp[3];
+    if (k < n) {
+      const int iy = box.z + (int)(k / bw), ix = box.x + (int)(k % bw);
+      p = ((long long)b * H + iy) * W + ix;
+      id = ids[p];
+      bp[0] = bary[3 * p]; bp[1] = bary[3 * p + 1]; bp[2] = bary[3 * p + 2];
+      if (pixel_is_covered(id, bp)) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) corners |= (__ldg(tris + 3 * (size_t)id + j) == v) << j;
+      }
+    }
+    const unsigned hits = __ballot_sync(0xffffffffu, corners != 0);
+    if (hits == 0u) continue;
+    if (corners != 0) {
+      PixelGrad pg;
+      const float *g_p = grad + (size_t)p * (FUSED ? A : 3);
+      pixel_grad<FUSED>(verts_b, attrs_b, tris, id, bp, g_p, A, pg);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (corners & (1 << j)) {
+          float *row = rows + ((size_t)lane * 3 + j) * ncomp;
+          row[0] = pg.terms[3 * j + 0]; row[1] = pg.terms[3 * j + 1]; row[2] = pg.terms[3 * j + 2];
+          if (FUSED)
+            for (int a = 0; a < A; ++a) row[3 + a] = (g_p[a] * pg.alpha) * pg.b[j];
+        }
+      }
+    }
+    __syncwarp();
+    // Fold in pixel order (ascending lane), corner order within a pixel.
+    unsigned todo = hits;
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int cm = __shfl_sync(0xffffffffu, corners, src);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (cm & (1 << j)) {
+          const float *row = rows + ((size_t)src * 3 + j) * ncomp;
+#pragma unroll
+          for (int s = 0; s < kMaxSlots; ++s) {
+            const int c = lane + 32 * s;
+            if (c < ncomp) acc[s] += row[c];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  if (d_verts != nullptr) {
+    float *dv = d_verts + (size_t)pair * 4;
+    if (lane < 3) dv[column_of(lane)] = acc[0];
+    if (lane == 3) dv[2] = 0.0f;        // z column never receives gradient
+  }
+  if (FUSED && d_attrs != nullptr) {
+    float *da = d_attrs + (size_t)pair * A;
+#pragma unroll
+    for (int s = 0; s < kMaxSlots; ++s) {
+      const int c = lane + 32 * s;
+      if (c >= 3 && c < ncomp) da[c - 3] = acc[s];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+
+int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, const float *verts,
+                  const float *attrs, const int32_t *tris, const int32_t *ids, const float *bary,
+                  int B, int V, int T, int A, int W, int H, float *d_verts, float *d_attrs, int mode,
+                  cudaStream_t stream) {
+  const bool fused = grad_image != nullptr;
+  const float *grad = fused ? grad_image : df_dbary;
+  const long long ppi = (long long)W * H, total = ppi * B;
+  const long long n_pairs = (long long)B * V;
+  if (n_pairs == 0) return PMR_OK;
+
+  if (mode == PMR_BACKWARD_ATOMIC) {
+    if (d_verts) PMR_CUDA(ctx, cudaMemsetAsync(d_verts, 0, (size_t)n_pairs * 4 * sizeof(float), stream));
+    if (fused && d_attrs) PMR_CUDA(ctx, cudaMemsetAsync(d_attrs, 0, (size_t)n_pairs * A * sizeof(float), stream));
+    if (total == 0 || T == 0) return PMR_OK;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+#define PMR_LAUNCH(F, AS)                                                                             \
+  backward_atomic_kernel<F, AS><<<grid, 256, 0, stream>>>(grad, verts, attrs, tris, ids, bary, V, A, ppi, \
+                                                          total, d_verts, d_attrs)
+    if (!fused) PMR_LAUNCH(false, 0);
+    else if (A == 9) PMR_LAUNCH(true, 9);
+    else if (A == 4) PMR_LAUNCH(true, 4);
+    else PMR_LAUNCH(true, 0);
+#undef PMR_LAUNCH
+    ctx->launches += 1;
+    return check_launch(ctx, "backward_atomic_kernel");
+  }
+
+  if (mode != PMR_BACKWARD_ORDERED) return set_error(ctx, PMR_ERR_INVALID, "unknown backward mode %d", mode);
+  if (fused && A > 125) return set_error(ctx, PMR_ERR_SIZE, "ordered backward supports at most 125 attributes");
+  int rc = ctx->scratch.reserve(ctx, (size_t)n_pairs * sizeof(int4));
+  if (rc) return rc;
+  int4 *vbox = (int4 *)ctx->scratch.ptr;
+  const float half_w = (float)(0.5 * W), half_h = (float)(0.5 * H);
+  vertex_box_init_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, stream>>>(vbox, n_pairs);
+  ctx->launches += 1;
+  if (T > 0 && total > 0) {
+    vertex_box_kernel<<<dim3((T + 255) / 256, B), 256, 0, stream>>>(verts, tris, V, T, W, H, half_w, half_h, vbox);
+    ctx->launches += 1;
+  }
+  const int ncomp = 3 + (fused ? A : 0);
+  const size_t smem = (size_t)kOrderedWarps * 32 * 3 * ncomp * sizeof(float);
+  const unsigned grid = (unsigned)((n_pairs + kOrderedWarps - 1) / kOrderedWarps);
+  if (fused) {
+    PMR_CUDA(ctx, cudaFuncSetAttribute(backward_ordered_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    backward_ordered_kernel<true><<<grid, kOrderedWarps * 32, smem, stream>>>(grad, verts, attrs, tris, ids, bary,
+                                                                            vbox, V, A, W, H, n_pairs, d_verts, d_attrs);
+  } else {
+    backward_ordered_kernel<false><<<grid, kOrderedWarps * 32, smem, stream>>>(grad, verts, attrs, tris, ids, bary,
+                                                                             vbox, V, A, W, H, n_pairs, d_verts, d_attrs);
+  }
+  ctx->launches += 1;
+  return check_launch(ctx, "backward_ordered_kernel");
+}
+
+}  // namespace pmr

@@ -1,0 +1,134 @@
+"""Tensor-level wrappers over the C ABI (include/pmr_b200.h): argument checks in the
+reference's terms, output allocation on the inputs' CUDA device, launch on torch's current
+stream.  No arithmetic happens in Python."""
+import torch
+
+from . import _lib
+
+_MODE_NAMES = {"atomic": _lib.BACKWARD_ATOMIC, "ordered": _lib.BACKWARD_ORDERED}
+
+
+def _require(t, dtype, what):
+    # The reference's accessor<> raises RuntimeError for a wrong scalar type
+    # (rasterize_triangles.cpp:323-328); keep type and wording.
+    if t.dtype != dtype:
+        names = {torch.float32: "Float", torch.int32: "Int"}
+        raise RuntimeError("expected scalar type %s but found %s for %s"
+                           % (names[dtype], str(t.dtype).replace("torch.", ""), what))
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor at this level" % what)
+    return t.contiguous()
+
+
+def _aligned(t):
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def mode_code(mode):
+    if isinstance(mode, str):
+        if mode not in _MODE_NAMES:
+            raise ValueError("backward mode must be 'atomic' or 'ordered', got %r" % (mode,))
+        return _MODE_NAMES[mode]
+    return int(mode)
+
+
+def rasterize_forward(vertices, triangles, image_width, image_height):
+    """vertices [B,V,4] f32, triangles [T,3] i32 -> ids [B,H,W] i32, bary [B,H,W,3], z [B,H,W]."""
+    v = _aligned(_require(vertices, torch.float32, "vertices"))
+    t = _require(triangles, torch.int32, "triangles")
+    B, V, _ = v.shape
+    W, H = int(image_width), int(image_height)
+    dev = v.device
+    ids = torch.empty((B, max(H, 0), max(W, 0)), dtype=torch.int32, device=dev)
+    bary = torch.empty((B, max(H, 0), max(W, 0), 3), dtype=torch.float32, device=dev)
+    z = torch.empty((B, max(H, 0), max(W, 0)), dtype=torch.float32, device=dev)
+    ctx = _lib.context(dev.index)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pmr_rasterize_forward(ctx, _lib.ptr(v), _lib.ptr(t), B, V, t.shape[0], W, H,
+                                               _lib.ptr(ids), _lib.ptr(bary), _lib.ptr(z), _lib.stream_ptr(dev))
+    _lib.check(ctx, rc)
+    return ids, bary, z
+
+
+def rasterize_backward(df_dbary, vertices, triangles, ids, bary, mode):
+    """-> df_dvertices [B,V,4]."""
+    v = _aligned(_require(vertices, torch.float32, "vertices"))
+    t = _require(triangles, torch.int32, "triangles")
+    g = _require(df_dbary, torch.float32, "df_dbarycentric_coords")
+    i = _require(ids, torch.int32, "px_triangle_ids")
+    b = _require(bary, torch.float32, "px_barycentric_coords")
+    B, V, _ = v.shape
+    H, W = i.shape[1], i.shape[2]
+    out = torch.empty((B, V, 4), dtype=torch.float32, device=v.device)
+    ctx = _lib.context(v.device.index)
+    with torch.cuda.device(v.device):
+        rc = _lib.load().pmr_rasterize_backward(ctx, _lib.ptr(g), _lib.ptr(v), _lib.ptr(t), _lib.ptr(i), _lib.ptr(b),
+                                                B, V, t.shape[0], W, H, _lib.ptr(out), mode_code(mode),
+                                                _lib.stream_ptr(v.device))
+    _lib.check(ctx, rc)
+    return out
+
+
+def interpolate_forward(attributes, triangles, ids, bary, background):
+    a = _require(attributes, torch.float32, "attributes")
+    t = _require(triangles, torch.int32, "triangles")
+    i = _require(ids, torch.int32, "px_triangle_ids")
+    b = _require(bary, torch.float32, "px_barycentric_coords")
+    bg = _require(background, torch.float32, "background_value")
+    B, V, A = a.shape
+    H, W = i.shape[1], i.shape[2]
+    out = torch.empty((B, H, W, A), dtype=torch.float32, device=a.device)
+    ctx = _lib.context(a.device.index)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().pmr_interpolate_forward(ctx, _lib.ptr(a), _lib.ptr(t), _lib.ptr(i), _lib.ptr(b), _lib.ptr(bg),
+                                                 B, V, t.shape[0], A, W, H, _lib.ptr(out), _lib.stream_ptr(a.device))
+    _lib.check(ctx, rc)
+    return out
+
+
+def rasterize_interpolate_forward(vertices, attributes, triangles, background, image_width, image_height):
+    """Fused rasterize_clip_space forward -> image [B,H,W,A], ids, bary, z."""
+    v = _aligned(_require(vertices, torch.float32, "clip_space_vertices"))
+    a = _require(attributes, torch.float32, "attributes")
+    t = _require(triangles, torch.int32, "triangles")
+    bg = _require(background, torch.float32, "background_value")
+    B, V, _ = v.shape
+    A = a.shape[2]
+    W, H = int(image_width), int(image_height)
+    dev = v.device
+    ids = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    bary = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+    z = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    image = torch.empty((B, H, W, A), dtype=torch.float32, device=dev)
+    ctx = _lib.context(dev.index)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pmr_rasterize_interpolate_forward(
+            ctx, _lib.ptr(v), _lib.ptr(a), _lib.ptr(t), _lib.ptr(bg), B, V, t.shape[0], A, W, H,
+            _lib.ptr(ids), _lib.ptr(bary), _lib.ptr(z), _lib.ptr(image), _lib.stream_ptr(dev))
+    _lib.check(ctx, rc)
+    return image, ids, bary, z
+
+
+def rasterize_interpolate_backward(grad_image, vertices, attributes, triangles, ids, bary, mode,
+                                   need_vertices=True, need_attributes=True):
+    """-> (d_vertices [B,V,4] or None, d_attributes [B,V,A] or None)."""
+    g = _require(grad_image, torch.float32, "grad_output")
+    v = _aligned(_require(vertices, torch.float32, "clip_space_vertices"))
+    a = _require(attributes, torch.float32, "attributes")
+    t = _require(triangles, torch.int32, "triangles")
+    i = _require(ids, torch.int32, "px_triangle_ids")
+    b = _require(bary, torch.float32, "px_barycentric_coords")
+    B, V, A = a.shape
+    H, W = i.shape[1], i.shape[2]
+    dev = v.device
+    dv = torch.empty((B, V, 4), dtype=torch.float32, device=dev) if need_vertices else None
+    da = torch.empty((B, V, A), dtype=torch.float32, device=dev) if need_attributes else None
+    ctx = _lib.context(dev.index)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pmr_rasterize_interpolate_backward(
+            ctx, _lib.ptr(g), _lib.ptr(v), _lib.ptr(a), _lib.ptr(t), _lib.ptr(i), _lib.ptr(b),
+            B, V, t.shape[0], A, W, H, _lib.ptr(dv), _lib.ptr(da), mode_code(mode), _lib.stream_ptr(dev))
+    _lib.check(ctx, rc)
+    return dv, da

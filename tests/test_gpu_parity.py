@@ -1,0 +1,263 @@
+"""Parity of the CUDA path (through the C ABI) against the reference golden vectors and the CPU
+oracle.  Bars (BASELINE.json north_star / BASELINE.md section 5):
+  * triangle ids, coverage: bit-exact;
+  * barycentrics, z, interpolated image: bit-exact is asserted (the kernels reproduce the
+    reference's rounding points; the stated tolerance 1e-6 + 1e-5*|ref| is the fallback bar and is
+    checked by assert_close where summation order legitimately differs);
+  * gradients in ORDERED mode: bit-exact (reference summation order);
+  * gradients in ATOMIC mode: compared with the fp64-accumulated evaluation of the same fp32 terms,
+    next to the reference's own distance from it.
+"""
+import ctypes
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import (GOLDEN_DIR, assert_bits, assert_close, golden_names, grad_from_seed, load_golden)
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+KERNEL_CASES = [n for n in golden_names() if "vertices" in np.load(os.path.join(GOLDEN_DIR, n + ".npz")).files
+                and not n.endswith("640x480")]
+FULL_CASES = [n for n in golden_names() if "clip_vertices" in np.load(os.path.join(GOLDEN_DIR, n + ".npz")).files
+              and not n.endswith("640x480")]
+DIGESTS = json.load(open(os.path.join(GOLDEN_DIR, "digests.json")))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def pmr():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pytorch_mesh_renderer_b200 as m
+    return m
+
+
+@pytest.fixture(params=[64, 0], ids=["small-mesh-path", "binned-path"])
+def threshold(request, pmr):
+    """Run every case through both forward paths: whole-mesh tiles and binned tile lists."""
+    from pytorch_mesh_renderer_b200 import _lib
+    ctx = _lib.context(torch.cuda.current_device())
+    _lib.load().pmr_set_small_mesh_threshold(ctx, request.param)
+    yield request.param
+    _lib.load().pmr_set_small_mesh_threshold(ctx, 64)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def atomic_close(actual, ref32, ref64, what):
+    """ATOMIC mode sums the same fp32 terms in another order: its distance from the exactly summed
+    value must be of the order of the reference's own distance from it."""
+    ref_err = np.abs(ref32.astype(np.float64) - ref64)
+    err = np.abs(actual.astype(np.float64) - ref64)
+    scale = np.abs(ref64).max() + 1e-30
+    bound = 1e-6 + 1e-5 * np.abs(ref64) + 8.0 * ref_err.max() + 4e-6 * scale
+    assert (err <= bound).all(), "%s: max err %g vs bound %g (reference's own max err %g)" % (
+        what, err.max(), bound.min(), ref_err.max())
+
+
+@pytest.mark.parametrize("name", KERNEL_CASES)
+def test_kernel_golden(pmr, oracle, threshold, name):
+    from pytorch_mesh_renderer_b200 import ops
+    c = load_golden(name)
+    W, H = int(c["width"]), int(c["height"])
+    v, t = dev(c["vertices"])[None], dev(c["triangles"])
+    ids, bary, z = ops.rasterize_forward(v, t, W, H)
+    assert_bits(ids[0].cpu().numpy(), c["ids"], "ids")
+    assert_bits(bary[0].cpu().numpy(), c["bary"], "bary")
+    assert_bits(z[0].cpu().numpy(), c["z"], "z")
+    g = dev(c["df_dbary"])[None]
+    dv = ops.rasterize_backward(g, v, t, dev(c["ids"])[None], dev(c["bary"])[None], "ordered")
+    assert_bits(dv[0].cpu().numpy(), c["df_dvertices"], "df_dvertices (ordered)")
+    dva = ops.rasterize_backward(g, v, t, dev(c["ids"])[None], dev(c["bary"])[None], "atomic")
+    ref64 = oracle.backward_f64acc(c["df_dbary"], c["vertices"], c["triangles"], c["ids"], c["bary"])
+    atomic_close(dva[0].cpu().numpy(), c["df_dvertices"], ref64, "df_dvertices (atomic)")
+    assert not dva[0, :, 2].any().item()
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_full_path_golden(pmr, oracle, threshold, name):
+    c = load_golden(name)
+    W, H = int(c["width"]), int(c["height"])
+    cv = dev(c["clip_vertices"]).requires_grad_(True)
+    at = dev(c["attributes"]).requires_grad_(True)
+    with pmr.backward_mode("ordered"):
+        out, (ids, bary, z) = pmr.rasterize_clip_space(cv, at, dev(c["triangles"]), W, H, dev(c["background"]),
+                                                        return_buffers=True)
+        out.backward(dev(c["grad_out"]))
+    assert_bits(ids.cpu().numpy(), c["ids"], "ids")
+    assert_bits(bary.detach().cpu().numpy(), c["bary"], "bary")
+    assert_bits(z.detach().cpu().numpy(), c["z"], "z")
+    assert_bits(out.detach().cpu().numpy(), c["out"], "out")
+    assert_bits(at.grad.cpu().numpy(), c["d_attributes"], "d_attributes (ordered)")
+    assert_bits(cv.grad.cpu().numpy(), c["d_clip_vertices"], "d_clip_vertices (ordered)")
+    # throughput mode
+    cv2 = dev(c["clip_vertices"]).requires_grad_(True)
+    at2 = dev(c["attributes"]).requires_grad_(True)
+    with pmr.backward_mode("atomic"):
+        out2 = pmr.rasterize_clip_space(cv2, at2, dev(c["triangles"]), W, H, dev(c["background"]))
+        out2.backward(dev(c["grad_out"]))
+    assert_bits(out2.detach().cpu().numpy(), c["out"], "out")
+    scale = np.abs(c["d_attributes"]).max()
+    assert np.abs(at2.grad.cpu().numpy() - c["d_attributes"]).max() <= 1e-6 + 2e-5 * scale
+    scale = np.abs(c["d_clip_vertices"]).max()
+    assert np.abs(cv2.grad.cpu().numpy() - c["d_clip_vertices"]).max() <= 1e-6 + 2e-5 * scale
+
+
+@pytest.mark.parametrize("name", ["simple_triangle", "perspective_triangle"])
+def test_reference_triangle_tests_640x480(pmr, threshold, name):
+    """rasterize_triangles_test.py:72-77 at the test's own resolution, digest-pinned."""
+    from pytorch_mesh_renderer_b200 import ops
+    c = load_golden(name + "_640x480")
+    v, t = dev(c["vertices"])[None], dev(c["triangles"])
+    ids, bary, z = ops.rasterize_forward(v, t, 640, 480)
+    d = DIGESTS[name]
+    assert sha(ids[0].cpu().numpy()) == d["ids"]
+    assert sha(bary[0].cpu().numpy()) == d["bary"]
+    assert sha(z[0].cpu().numpy()) == d["z"]
+    g = dev(grad_from_seed(c["df_dbary_seed"], (480, 640, 3)))[None]
+    dv = ops.rasterize_backward(g, v, t, ids, bary, "ordered")
+    assert_bits(dv[0].cpu().numpy(), c["df_dvertices"], "df_dvertices")
+
+
+@pytest.mark.parametrize("name", ["two_cubes", "c1_cube"])
+def test_reference_cube_tests_640x480(pmr, threshold, name):
+    """rasterize_triangles_test.py:79-117 (A=4) and BASELINE config c1 (A=9) at 2 x 640x480."""
+    c = load_golden(name + "_640x480")
+    A = c["attributes"].shape[2]
+    g = dev(grad_from_seed(c["grad_out_seed"], (2, 480, 640, A)))
+    cv = dev(c["clip_vertices"]).requires_grad_(True)
+    at = dev(c["attributes"]).requires_grad_(True)
+    with pmr.backward_mode("ordered"):
+        out, (ids, bary, z) = pmr.rasterize_clip_space(cv, at, dev(c["triangles"]), 640, 480, dev(c["background"]),
+                                                        return_buffers=True)
+        out.backward(g)
+    d = DIGESTS[name]
+    assert sha(ids.cpu().numpy()) == d["ids"]
+    assert sha(bary.detach().cpu().numpy()) == d["bary"]
+    assert sha(z.detach().cpu().numpy()) == d["z"]
+    assert sha(out.detach().cpu().numpy()) == d["out"]
+    assert_bits(at.grad.cpu().numpy(), c["d_attributes"], "d_attributes")
+    assert_bits(cv.grad.cpu().numpy(), c["d_clip_vertices"], "d_clip_vertices")
+
+
+def test_reference_png_fixtures(pmr):
+    """The PNG fixtures of rasterize_triangles_test.py:72-117 under its comparison rule
+    (test_utils.py:105-160): at most 0.1 % of pixels off by more than 0.01."""
+    from PIL import Image
+
+    def near(image, name):
+        png = np.asarray(Image.open(os.path.join(GOLDEN_DIR, "reference_png", name))).astype(np.float64) / 255.0
+        diff = np.abs(png - np.clip(image, 0.0, 1.0))
+        return np.any(diff > 0.01, axis=2).mean() <= 0.001
+
+    for case, png in (("simple_triangle", "Simple_Triangle.png"),
+                      ("perspective_triangle", "Perspective_Corrected_Triangle.png")):
+        c = load_golden(case + "_640x480")
+        # CPU tensors in, CPU tensors out: the reference test's own calling convention.
+        _, bary, _ = pmr.rasterize_barycentric(torch.from_numpy(c["vertices"]), torch.from_numpy(c["triangles"]), 640, 480)
+        assert bary.device.type == "cpu" and bary.shape == (480, 640, 3)
+        assert near(np.concatenate([bary.numpy(), np.ones((480, 640, 1), np.float32)], 2), png)
+    c = load_golden("two_cubes_640x480")
+    out = pmr.rasterize(torch.from_numpy(c["world_vertices"]), torch.from_numpy(c["attributes"]),
+                        torch.from_numpy(c["triangles"]), torch.from_numpy(c["camera_matrices"]), 640, 480,
+                        torch.from_numpy(c["background"]))
+    for i in (0, 1):
+        assert near(out[i].numpy(), "Unlit_Cube_%d.png" % i)
+
+
+def test_barycentric_rasterizer_signature(pmr):
+    """ext.py:8,43,63: (vertices[V,4], triangles, W, H) -> (ids, bary, z); backward returns
+    (df_dvertices, zeros_like(triangles), None, None)."""
+    c = load_golden("jacobian_cube_28x21")
+    v = dev(c["vertices"]).requires_grad_(True)
+    t = dev(c["triangles"])
+    with pmr.backward_mode("ordered"):
+        ids, bary, z = pmr.BarycentricRasterizer.apply(v, t, 28, 21)
+        assert ids.shape == (21, 28) and ids.dtype == torch.int32 and bary.shape == (21, 28, 3) and z.shape == (21, 28)
+        bary.backward(dev(c["df_dbary"]))
+    assert_bits(v.grad.cpu().numpy(), c["df_dvertices"], "df_dvertices")
+
+
+def test_error_behaviour(pmr):
+    v = torch.zeros(1, 3, 4, device="cuda"); a = torch.zeros(1, 3, 2, device="cuda")
+    t = torch.zeros(1, 3, dtype=torch.int32, device="cuda"); bg = torch.zeros(2, device="cuda")
+    with pytest.raises(ValueError, match="Image width must be > 0"):
+        pmr.rasterize_clip_space(v, a, t, 0, 4, bg)
+    with pytest.raises(ValueError, match="Image height must be > 0"):
+        pmr.rasterize_clip_space(v, a, t, 4, -1, bg)
+    with pytest.raises(ValueError, match="must be 3D"):
+        pmr.rasterize_clip_space(v[0], a, t, 4, 4, bg)
+    with pytest.raises(RuntimeError, match="expected scalar type Int"):
+        pmr.rasterize_clip_space(v, a, t.long(), 4, 4, bg)
+    with pytest.raises(RuntimeError, match="expected scalar type Float"):
+        pmr.rasterize_barycentric(v[0].double(), t, 4, 4)
+
+
+def test_sphere_views_vs_oracle(pmr, oracle):
+    """A reduced c2: 3 120-triangle UV sphere, 3 views, 160x160, A=9 -- binned path, shared edges,
+    both windings, pole fans."""
+    from pytorch_mesh_renderer_b200 import synthetic as S
+    sc = S.sphere_views(40, 39, 3, 160)
+    g = S.upstream_gradient((3, 160, 160, 9))
+    ref = oracle.rasterize_clip_space(sc["clip_vertices"], sc["attributes"], sc["triangles"], 160, 160,
+                                      sc["background"], grad_out=g)
+    cv = dev(sc["clip_vertices"]).requires_grad_(True)
+    at = dev(sc["attributes"]).requires_grad_(True)
+    with pmr.backward_mode("ordered"):
+        out, (ids, bary, z) = pmr.rasterize_clip_space(cv, at, dev(sc["triangles"]), 160, 160, dev(sc["background"]),
+                                                        return_buffers=True)
+        out.backward(dev(g))
+    assert_bits(ids.cpu().numpy(), ref["ids"], "ids")
+    assert_bits(bary.detach().cpu().numpy(), ref["bary"], "bary")
+    assert_bits(z.detach().cpu().numpy(), ref["z"], "z")
+    assert_bits(out.detach().cpu().numpy(), ref["out"], "out")
+    assert_bits(at.grad.cpu().numpy(), ref["d_attributes"], "d_attributes")
+    assert_bits(cv.grad.cpu().numpy(), ref["d_vertices"], "d_vertices")
+    cv2 = dev(sc["clip_vertices"]).requires_grad_(True)
+    at2 = dev(sc["attributes"]).requires_grad_(True)
+    with pmr.backward_mode("atomic"):
+        pmr.rasterize_clip_space(cv2, at2, dev(sc["triangles"]), 160, 160, dev(sc["background"])).backward(dev(g))
+    assert_close(at2.grad.cpu().numpy(), ref["d_attributes"], "d_attributes (atomic)")
+    assert_close(cv2.grad.cpu().numpy(), ref["d_vertices"], "d_vertices (atomic)")
+
+
+def test_occlusion_soup_vs_oracle(pmr, oracle):
+    """A reduced c5: 300 large overlapping triangles (depth complexity ~10), 2 x 192x192."""
+    from pytorch_mesh_renderer_b200 import synthetic as S
+    sc = S.occlusion_soup(2, 192, n_triangles=300, scale=0.4)
+    ref = oracle.rasterize_clip_space(sc["clip_vertices"], sc["attributes"], sc["triangles"], 192, 192, sc["background"])
+    out, (ids, bary, z) = pmr.rasterize_clip_space(dev(sc["clip_vertices"]), dev(sc["attributes"]), dev(sc["triangles"]),
+                                                   192, 192, dev(sc["background"]), return_buffers=True)
+    assert_bits(ids.cpu().numpy(), ref["ids"], "ids")
+    assert_bits(bary.cpu().numpy(), ref["bary"], "bary")
+    assert_bits(z.cpu().numpy(), ref["z"], "z")
+    assert_bits(out.cpu().numpy(), ref["out"], "out")
+
+
+def test_c_abi_host_entry_point(pmr, oracle):
+    """pmr_rasterize_clip_space_host with plain numpy host buffers (what bench.py times as e2e)."""
+    from pytorch_mesh_renderer_b200 import _lib
+    c = load_golden("full_grid_A9_64x64")
+    L = _lib.load()
+    ctx = _lib.context(torch.cuda.current_device())
+    B, V, A = c["attributes"].shape
+    T = c["triangles"].shape[0]
+    out = np.empty_like(c["out"]); dv = np.empty_like(c["d_clip_vertices"]); da = np.empty_like(c["d_attributes"])
+    ids = np.empty_like(c["ids"]); bary = np.empty_like(c["bary"]); z = np.empty_like(c["z"])
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    arrs = [np.ascontiguousarray(c[k]) for k in ("clip_vertices", "attributes", "triangles", "background", "grad_out")]
+    rc = L.pmr_rasterize_clip_space_host(ctx, *[p(a) for a in arrs], B, V, T, A, 64, 64, p(out), p(dv), p(da),
+                                         p(ids), p(bary), p(z), _lib.BACKWARD_ORDERED, ctypes.c_void_p(0))
+    assert rc == 0, L.pmr_last_error(ctx)
+    assert_bits(ids, c["ids"], "ids"); assert_bits(out, c["out"], "out")
+    assert_bits(dv, c["d_clip_vertices"], "d_clip_vertices"); assert_bits(da, c["d_attributes"], "d_attributes")
