@@ -1,0 +1,323 @@
+"""bench.py -- fwd+bwd Mpixels/s of rasterize+interpolate (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one batch: fused rasterize+interpolate forward
+(ids, barycentrics, z, attribute image) and its backward (gradients to clip-space vertices and
+attributes), A = 9 attributes.  N = 1 runs BASELINE.json configs[1] (c2: 50 244-triangle UV sphere,
+64 views x 512^2).  N > 1: one process per GPU (torchrun), every rank runs the same per-GPU batch
+(weak scaling), the views share one mesh, so each step ends with the on-device reduction of the
+per-view clip-space gradients to one world-space [V,3] gradient and ONE NCCL all-reduce of it
+(SURVEY.md section 8e); value = pixels of all ranks / max-over-ranks time.
+
+Prints ONE JSON line (rank 0).  --impl reference times the reference's own CPU implementation
+(oracle/_ref kernel + the reference's torch-op interpolation chain) on the host cores instead.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd Mpixels/s (rasterize+interpolate)"
+UNIT = "Mpixels/s"
+A = 9
+
+WORKLOADS = {
+    "c1": "c1: 12-triangle cube test scene, batch 2 x 640x480, A=9",
+    "c2": "c2: 50244-triangle UV sphere, batch 64 x 512x512, A=9",
+    "c3": "c3: 1001112-triangle UV sphere, batch 16 x 1024x1024, A=9",
+    "c4": "c4: 99904-triangle UV sphere shared by 256 views x 512x512, A=9",
+    "c5": "c5: 2000 large overlapping triangles (depth complexity ~50), batch 32 x 2048x2048, A=9",
+}
+
+
+def make_workload(name, batch_override=None):
+    from pytorch_mesh_renderer_b200 import synthetic as S
+    if name == "c1":
+        return S.cube_test_scene()
+    if name == "c2":
+        return S.sphere_views(159, 158, batch_override or 64, 512)
+    if name == "c3":
+        return S.sphere_views(708, 707, batch_override or 16, 1024)
+    if name == "c4":
+        return S.sphere_views(224, 223, batch_override or 256, 512)
+    if name == "c5":
+        return S.occlusion_soup(batch_override or 32, 2048)
+    raise ValueError(name)
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle.cpu_reference import CpuReference
+    sc = make_workload(args.config)
+    ref = CpuReference(args.config)
+    per_step = ref.cores
+    for _ in range(max(args.warmup, 1)):
+        ref.timed(per_step)
+    px = secs = 0.0
+    for _ in range(args.steps):
+        p, s = ref.timed(per_step)
+        px += p
+        secs += s
+    ref.close()
+    value = px / secs / 1e6
+    H, W = sc["height"], sc["width"]
+    sample = "%d images of %dx%d per step (one per worker process), %d steps" % (per_step, W, H, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "attributes": A},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch (diagnostics only)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="atomic", choices=["atomic", "ordered"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import pytorch_mesh_renderer_b200 as pmr
+    from pytorch_mesh_renderer_b200 import _lib, ops
+
+    # CPU baseline first (rank 0, N = 1 only): worker processes are spawned before CUDA is touched.
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_reference import CpuReference
+        ref = CpuReference(args.config)
+        ref.warm()
+        n_img = {"c1": 2 * ref.cores, "c2": 4 * ref.cores, "c3": ref.cores, "c4": 4 * ref.cores, "c5": ref.cores}[args.config]
+        px, secs = ref.timed(n_img)
+        ref.close()
+        cpu_baseline = {"value": px / secs / 1e6, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                        "sample": "%d images of the workload, one worker process per core, %.1f s wall" % (n_img, secs)}
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    sc = make_workload(args.config, args.batch)
+    B, V = sc["clip_vertices"].shape[:2]
+    T = sc["triangles"].shape[0]
+    H, W = sc["height"], sc["width"]
+    P = B * H * W
+    g_host = np.random.default_rng(1).standard_normal((B, H, W, A), dtype=np.float32)
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    clip, attrs, tris, bg = (to_dev(sc[k]) for k in ("clip_vertices", "attributes", "triangles", "background"))
+    grad = to_dev(g_host)
+    shared_mesh = world > 1
+    mvp = to_dev(sc["camera_matrices"]) if shared_mesh and "camera_matrices" in sc else None
+
+    def step():
+        cv = clip.detach().requires_grad_(True)
+        at = attrs.detach().requires_grad_(True)
+        out = pmr.rasterize_clip_space(cv, at, tris, W, H, bg)
+        out.backward(grad)
+        if mvp is not None:
+            # multi-view fitting: d(clip) -> d(world) through the view matrices, summed over the local
+            # views, then one all-reduce of [V,3] over NVLink.
+            d_world = torch.einsum("bvj,bjk->vk", cv.grad, mvp[:, :, :3])
+            dist.all_reduce(d_world)
+            return d_world
+        return cv.grad
+
+    with pmr.backward_mode(args.mode):
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        _lib.enable_stage_timing(local_rank, True)
+        _lib.read_stage_timing(local_rank, reset=True)
+        launches0 = _lib.launch_count(local_rank)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms_total = e0.elapsed_time(e1)
+        launches = _lib.launch_count(local_rank) - launches0
+        stages = _lib.read_stage_timing(local_rank, reset=True)
+        _lib.enable_stage_timing(local_rank, False)
+        clocks = sampler.stop()
+
+    if world > 1:
+        t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * P / (ms_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (device time from the library's per-stage CUDA events)
+    peak, peak_src = measured_peak_gbs()
+    bytes_fwd = P * (20 + 4 * A) + B * (V * (16 + 4 * A) + 12 * T)
+    bytes_bwd = P * (16 + 4 * A) + B * V * (16 + 4 * A)
+    stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
+    dominant = "backward" if stage_ms["backward"] >= stage_ms["raster"] else "raster"
+    dom_bytes = bytes_bwd if dominant == "backward" else bytes_fwd
+    achieved = dom_bytes / (stage_ms[dominant] * 1e-3) / 1e9 if stage_ms[dominant] > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": {"raster": "raster_tile_kernel<9> (forward + fused interpolation)",
+                                   "backward": "backward_%s_kernel (fused interpolation backward)" % args.mode}[dominant],
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": stage_ms[dominant],
+        "stages_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+        "step": {"algorithmic_bytes": bytes_fwd + bytes_bwd,
+                 "achieved": (bytes_fwd + bytes_bwd) / (ms_step * 1e-3) / 1e9,
+                 "frac": (bytes_fwd + bytes_bwd) / (ms_step * 1e-3) / 1e9 / peak},
+    }
+
+    # ---- e2e: the C-ABI host entry point, pinned host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        L = _lib.load()
+        ctx = _lib.context(local_rank)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h_v, h_a, h_t, h_bg, h_g = pin(sc["clip_vertices"]), pin(sc["attributes"]), pin(sc["triangles"]), pin(sc["background"]), pin(g_host)
+        h_out = torch.empty((B, H, W, A), dtype=torch.float32).pin_memory()
+        h_dv = torch.empty((B, V, 4), dtype=torch.float32).pin_memory()
+        h_da = torch.empty((B, V, A), dtype=torch.float32).pin_memory()
+        p = lambda t_: ctypes.c_void_p(t_.data_ptr())
+        mode = _lib.BACKWARD_ATOMIC if args.mode == "atomic" else _lib.BACKWARD_ORDERED
+        stream = torch.cuda.current_stream(device)
+
+        def host_step():
+            rc = L.pmr_rasterize_clip_space_host(ctx, p(h_v), p(h_a), p(h_t), p(h_bg), p(h_g), B, V, T, A, W, H,
+                                                 p(h_out), p(h_dv), p(h_da), None, None, None, mode,
+                                                 ctypes.c_void_p(stream.cuda_stream))
+            _lib.check(ctx, rc)
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            host_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_step()
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([secs], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        h2d = h_v.numel() * 4 + h_a.numel() * 4 + h_t.numel() * 4 + h_bg.numel() * 4 + h_g.numel() * 4
+        d2h = h_out.numel() * 4 + h_dv.numel() * 4 + h_da.numel() * 4
+        e2e = {"value": world * P * e2e_steps / secs / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * secs / e2e_steps,
+               "call": "pmr_rasterize_clip_space_host (C ABI, pinned host buffers in, host buffers out)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.config], "per_gpu_batch": B, "triangles": T, "vertices": V,
+                       "image": [H, W], "attributes": A, "backward_mode": args.mode,
+                       "triangles_per_s": world * B * T / (ms_step * 1e-3),
+                       "l2": "per-step working set %.2f GB exceeds the 126 MB L2; no explicit flush" % ((bytes_fwd + bytes_bwd) / 1e9),
+                       "collective": "all_reduce(sum) of world-space vertex gradient [V,3] per step" if shared_mesh else "none"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,22 @@ PMR_API unsigned long long pmr_last_bin_entries(const pmr_context *ctx);
 PMR_API int pmr_set_small_mesh_threshold(pmr_context *ctx, int triangles);
 
 /*
+ * Per-stage device timing (CUDA events recorded on the launching stream around each stage while
+ * enabled).  bench.py uses it to attribute step time to kernels for the roofline report.
+ * pmr_read_stage_timing waits for the recorded events, ADDS the elapsed milliseconds and the
+ * number of timed intervals per stage into ms[PMR_STAGE_COUNT] / counts[PMR_STAGE_COUNT]'s
+ * running totals held by the context, copies the totals out and, if `reset` is non-zero,
+ * clears them.
+ */
+#define PMR_STAGE_BIN 0      /* bin_count + bin_offsets + length read-back + bin_fill */
+#define PMR_STAGE_RASTER 1   /* raster_tile_kernel (with fused interpolation when requested) */
+#define PMR_STAGE_BACKWARD 2 /* backward kernels (atomic: one kernel; ordered: boxes + gather) */
+#define PMR_STAGE_INTERP 3   /* standalone interpolate_kernel */
+#define PMR_STAGE_COUNT 4
+PMR_API int pmr_enable_stage_timing(pmr_context *ctx, int enable);
+PMR_API int pmr_read_stage_timing(pmr_context *ctx, double *ms, long long *counts, int reset);
+
+/*
  * rasterize_triangles forward.  Replaces rasterize_triangles_cpp.forward
  * (rasterize_triangles.cpp:302-419) for B images at once.
  */

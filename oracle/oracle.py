@@ -126,12 +126,39 @@ def interp_backward(grad_out, attributes, triangles, ids, bary, background):
     return dattr, dbary
 
 
+def interp_backward_attributes_f64acc(grad_out, triangles, ids, bary, vertex_count):
+    """d_attributes with the same fp32 products g_a*alpha*b_k but summed in double (yardstick for
+    the atomic mode)."""
+    g, t, i, b = _f32(grad_out), _i32(triangles), _i32(ids).reshape(-1), _f32(bary).reshape(-1, 3)
+    A = g.shape[-1]
+    g = g.reshape(-1, A)
+    s = (np.float32(2.0) * b[:, 0] + np.float32(2.0) * b[:, 1]) + np.float32(2.0) * b[:, 2]
+    alpha = np.clip(s, np.float32(0.0), np.float32(1.0)).astype(np.float32)
+    d_img = (g * alpha[:, None]).astype(np.float32)
+    out = np.zeros((vertex_count, A), np.float64)
+    if t.shape[0] == 0:
+        return out
+    for k in range(3):
+        np.add.at(out, t[i, k], (d_img * b[:, k:k + 1]).astype(np.float32).astype(np.float64))
+    return out
+
+
+def atomic_mode_bound(ref32, ref64, slack=8.0):
+    """Per-entry bound for a result that sums the reference's fp32 terms in another order: the
+    north-star tolerance around the exactly summed value plus `slack` times the reference's own
+    worst distance from it (the reference is itself only one particular fp32 order)."""
+    ref_err = np.abs(np.asarray(ref32, np.float64) - ref64).max() if ref64.size else 0.0
+    scale = np.abs(ref64).max() if ref64.size else 0.0
+    return 1e-6 + 1e-5 * np.abs(ref64) + slack * ref_err + 4e-6 * scale
+
+
 def rasterize_clip_space(clip_space_vertices, attributes, triangles, image_width, image_height,
-                         background_value, grad_out=None):
+                         background_value, grad_out=None, f64_yardstick=False):
     """Batched restatement of rast.py:66-152 (a Python loop over images, like rast.py:112).
 
     Returns dict(out, ids, bary, z) and, when grad_out [B,H,W,A] is given, also
-    d_vertices [B,V,4] and d_attributes [B,V,A].
+    d_vertices [B,V,4] and d_attributes [B,V,A] (plus their double-accumulated versions when
+    f64_yardstick is set).
     """
     cv, at, tr = _f32(clip_space_vertices), _f32(attributes), _i32(triangles)
     bg = _f32(np.broadcast_to(np.asarray(background_value, np.float32), (at.shape[2],)))
@@ -139,6 +166,8 @@ def rasterize_clip_space(clip_space_vertices, attributes, triangles, image_width
     res = dict(out=[], ids=[], bary=[], z=[])
     if grad_out is not None:
         res.update(d_vertices=[], d_attributes=[])
+        if f64_yardstick:
+            res.update(d_vertices_f64=[], d_attributes_f64=[])
     for b in range(B):
         ids, bary, z = forward(cv[b], tr, image_width, image_height)
         res["ids"].append(ids)
@@ -149,4 +178,8 @@ def rasterize_clip_space(clip_space_vertices, attributes, triangles, image_width
             dattr, dbary = interp_backward(grad_out[b], at[b], tr, ids, bary, bg)
             res["d_attributes"].append(dattr)
             res["d_vertices"].append(backward(dbary, cv[b], tr, ids, bary))
+            if f64_yardstick:
+                res["d_vertices_f64"].append(backward_f64acc(dbary, cv[b], tr, ids, bary))
+                res["d_attributes_f64"].append(
+                    interp_backward_attributes_f64acc(grad_out[b], tr, ids, bary, cv.shape[1]))
     return {k: np.stack(v) for k, v in res.items()}

@@ -31,6 +31,8 @@ _PROTOTYPES = {
     "pmr_launch_count": (ctypes.c_longlong, [_vp]),
     "pmr_last_bin_entries": (ctypes.c_ulonglong, [_vp]),
     "pmr_set_small_mesh_threshold": (ctypes.c_int, [_vp, _i]),
+    "pmr_enable_stage_timing": (ctypes.c_int, [_vp, _i]),
+    "pmr_read_stage_timing": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), _i]),
     "pmr_rasterize_forward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pmr_rasterize_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pmr_interpolate_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -107,3 +109,19 @@ def launch_count(device_index=None):
         return sum(lib.pmr_launch_count(c) for c in _contexts.values())
     c = _contexts.get(device_index)
     return lib.pmr_launch_count(c) if c is not None else 0
+
+
+STAGES = ("bin", "raster", "backward", "interp")
+
+
+def enable_stage_timing(device_index, on=True):
+    check(context(device_index), load().pmr_enable_stage_timing(context(device_index), int(bool(on))))
+
+
+def read_stage_timing(device_index, reset=True):
+    """{stage: (total_ms, intervals)} accumulated since the last reset."""
+    ms = (ctypes.c_double * len(STAGES))()
+    n = (ctypes.c_longlong * len(STAGES))()
+    ctx = context(device_index)
+    check(ctx, load().pmr_read_stage_timing(ctx, ms, n, int(bool(reset))))
+    return {name: (ms[k], n[k]) for k, name in enumerate(STAGES)}

@@ -54,6 +54,31 @@ void Buffer::release() {
   bytes = 0;
 }
 
+static cudaEvent_t take_event(Context *ctx) {
+  cudaEvent_t e = nullptr;
+  if (!ctx->spare_events.empty()) {
+    e = ctx->spare_events.back();
+    ctx->spare_events.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+
+StageScope::StageScope(Context *c, int stage, cudaStream_t s) : ctx(c), stream(s), active(c && c->timing) {
+  if (!active) return;
+  iv.stage = stage;
+  iv.begin = take_event(ctx);
+  iv.end = take_event(ctx);
+  cudaEventRecord(iv.begin, stream);
+}
+
+StageScope::~StageScope() {
+  if (!active) return;
+  cudaEventRecord(iv.end, stream);
+  ctx->intervals.push_back(iv);
+}
+
 static int validate_common(Context *ctx, int B, int V, int T, int W, int H) {
   if (!ctx) return PMR_ERR_INVALID;
   if (B < 0 || V < 0 || T < 0) return set_error(ctx, PMR_ERR_INVALID, "negative batch/vertex/triangle count");
@@ -104,12 +129,40 @@ void pmr_destroy(pmr_context *ctx) {
   ctx->lists.release();
   ctx->scratch.release();
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+  for (const pmr::StageInterval &iv : ctx->intervals) { cudaEventDestroy(iv.begin); cudaEventDestroy(iv.end); }
+  for (cudaEvent_t e : ctx->spare_events) cudaEventDestroy(e);
   delete ctx;
 }
 
 const char *pmr_last_error(const pmr_context *ctx) { return ctx ? ctx->error : "null context"; }
 long long pmr_launch_count(const pmr_context *ctx) { return ctx ? ctx->launches : 0; }
 unsigned long long pmr_last_bin_entries(const pmr_context *ctx) { return ctx ? ctx->last_bin_entries : 0; }
+
+int pmr_enable_stage_timing(pmr_context *ctx, int enable) {
+  if (!ctx) return PMR_ERR_INVALID;
+  ctx->timing = enable != 0;
+  return PMR_OK;
+}
+
+int pmr_read_stage_timing(pmr_context *ctx, double *ms, long long *counts, int reset) {
+  if (!ctx) return PMR_ERR_INVALID;
+  for (const pmr::StageInterval &iv : ctx->intervals) {
+    float t = 0.0f;
+    PMR_CUDA(ctx, cudaEventSynchronize(iv.end));
+    PMR_CUDA(ctx, cudaEventElapsedTime(&t, iv.begin, iv.end));
+    ctx->stage_ms[iv.stage] += t;
+    ctx->stage_n[iv.stage] += 1;
+    ctx->spare_events.push_back(iv.begin);
+    ctx->spare_events.push_back(iv.end);
+  }
+  ctx->intervals.clear();
+  for (int k = 0; k < PMR_STAGE_COUNT; ++k) {
+    if (ms) ms[k] = ctx->stage_ms[k];
+    if (counts) counts[k] = ctx->stage_n[k];
+    if (reset) { ctx->stage_ms[k] = 0.0; ctx->stage_n[k] = 0; }
+  }
+  return PMR_OK;
+}
 
 int pmr_set_small_mesh_threshold(pmr_context *ctx, int triangles) {
   if (!ctx || triangles < 0) return PMR_ERR_INVALID;

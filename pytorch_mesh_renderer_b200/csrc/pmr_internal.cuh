@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/pmr_b200.h"
 
 namespace pmr {
@@ -25,6 +27,11 @@ struct Buffer {
   void release();
 };
 
+struct StageInterval {
+  cudaEvent_t begin, end;
+  int stage;
+};
+
 struct Context {
   int device = 0;
   int sm_count = 148;
@@ -34,6 +41,22 @@ struct Context {
   unsigned long long last_bin_entries = 0;
   long long launches = 0;             // kernels launched through this context (bench gpu_launches)
   char error[512] = {0};
+  // stage timing (pmr_enable_stage_timing)
+  bool timing = false;
+  std::vector<StageInterval> intervals;     // recorded, not yet read
+  std::vector<cudaEvent_t> spare_events;
+  double stage_ms[PMR_STAGE_COUNT] = {0, 0, 0, 0};
+  long long stage_n[PMR_STAGE_COUNT] = {0, 0, 0, 0};
+};
+
+// RAII bracket around one stage: records an event pair on `stream` when timing is enabled.
+struct StageScope {
+  Context *ctx;
+  cudaStream_t stream;
+  StageInterval iv;
+  bool active;
+  StageScope(Context *c, int stage, cudaStream_t s);
+  ~StageScope();
 };
 
 int check_launch(Context *ctx, const char *what);

@@ -306,6 +306,7 @@ int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, 
   const long long ppi = (long long)W * H, total = ppi * B;
   const long long n_pairs = (long long)B * V;
   if (n_pairs == 0) return PMR_OK;
+  StageScope timed(ctx, PMR_STAGE_BACKWARD, stream);
 
   if (mode == PMR_BACKWARD_ATOMIC) {
     if (d_verts) PMR_CUDA(ctx, cudaMemsetAsync(d_verts, 0, (size_t)n_pairs * 4 * sizeof(float), stream));

@@ -291,6 +291,7 @@ static int launch_raster(Context *ctx, const float *verts, const int32_t *tris, 
   const int tiles = tiles_x * tiles_y;
   const float half_w = (float)(0.5 * W), half_h = (float)(0.5 * H);   // K.cpp:309-310
   dim3 grid(tiles, B);
+  StageScope timed(ctx, PMR_STAGE_RASTER, stream);
 #define PMR_LAUNCH(AS)                                                                              \
   raster_tile_kernel<AS><<<grid, kChunk, 0, stream>>>(verts, tris, V, T, W, H, half_w, half_h,      \
                                                      tiles_x, tiles, counts, offsets, lists, ids,   \
@@ -320,15 +321,19 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
   }
 
   const size_t n_tiles = (size_t)B * tiles;
+  int32_t *lists = nullptr;
+  int *counts = nullptr, *offsets = nullptr;
+  {
+  StageScope timed(ctx, PMR_STAGE_BIN, stream);
   if (n_tiles > (size_t)INT_MAX) return set_error(ctx, PMR_ERR_SIZE, "too many screen tiles");
   // workspace: [total u64 | counts | cursors | offsets | ranges]
   int rc = ctx->bins.reserve(ctx, 16 + n_tiles * 3 * sizeof(int) + (size_t)B * T * sizeof(uint2) + 64);
   if (rc) return rc;
   char *base = (char *)ctx->bins.ptr;
   unsigned long long *total = (unsigned long long *)base;
-  int *counts = (int *)(base + 16);
+  counts = (int *)(base + 16);
   int *cursors = counts + n_tiles;
-  int *offsets = cursors + n_tiles;
+  offsets = cursors + n_tiles;
   uint2 *ranges = (uint2 *)(((uintptr_t)(offsets + n_tiles) + 15) & ~(uintptr_t)15);
 
   PMR_CUDA(ctx, cudaMemsetAsync(base, 0, 16 + n_tiles * 2 * sizeof(int), stream));
@@ -350,12 +355,13 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
   if (n_entries >= (1ull << 31)) return set_error(ctx, PMR_ERR_SIZE, "tile lists exceed 2^31 entries");
   rc = ctx->lists.reserve(ctx, (size_t)(n_entries + 1) * sizeof(int32_t));
   if (rc) return rc;
-  int32_t *lists = (int32_t *)ctx->lists.ptr;
+  lists = (int32_t *)ctx->lists.ptr;
 
   bin_fill_kernel<<<tgrid, 256, 0, stream>>>(ranges, T, tiles_x, tiles, offsets, cursors, lists);
   ctx->launches += 1;
   rc = check_launch(ctx, "bin_fill_kernel");
   if (rc) return rc;
+  }
   return launch_raster(ctx, verts, tris, B, V, T, W, H, counts, offsets, lists, ids, bary, z, attrs, bg, A,
                        image, stream);
 }
@@ -365,6 +371,7 @@ int interpolate_impl(Context *ctx, const float *attrs, const int32_t *tris, cons
                      cudaStream_t stream) {
   const long long ppi = (long long)W * H, total = ppi * B;
   if (total == 0 || A == 0) return PMR_OK;
+  StageScope timed(ctx, PMR_STAGE_INTERP, stream);
   interpolate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(attrs, tris, ids, bary, bg, V, A,
                                                                          ppi, total, out);
   ctx->launches += 1;

@@ -16,7 +16,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import (GOLDEN_DIR, assert_bits, assert_close, golden_names, grad_from_seed, load_golden)
+from conftest import GOLDEN_DIR, assert_bits, golden_names, grad_from_seed, load_golden
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -56,13 +56,12 @@ def dev(a):
 
 def atomic_close(actual, ref32, ref64, what):
     """ATOMIC mode sums the same fp32 terms in another order: its distance from the exactly summed
-    value must be of the order of the reference's own distance from it."""
-    ref_err = np.abs(ref32.astype(np.float64) - ref64)
-    err = np.abs(actual.astype(np.float64) - ref64)
-    scale = np.abs(ref64).max() + 1e-30
-    bound = 1e-6 + 1e-5 * np.abs(ref64) + 8.0 * ref_err.max() + 4e-6 * scale
+    value must be of the order of the reference's own distance from it (oracle.atomic_mode_bound)."""
+    from oracle import oracle as o
+    err = np.abs(np.asarray(actual, np.float64) - ref64)
+    bound = o.atomic_mode_bound(ref32, ref64)
     assert (err <= bound).all(), "%s: max err %g vs bound %g (reference's own max err %g)" % (
-        what, err.max(), bound.min(), ref_err.max())
+        what, err.max(), bound.min(), np.abs(np.asarray(ref32, np.float64) - ref64).max())
 
 
 @pytest.mark.parametrize("name", KERNEL_CASES)
@@ -107,10 +106,10 @@ def test_full_path_golden(pmr, oracle, threshold, name):
         out2 = pmr.rasterize_clip_space(cv2, at2, dev(c["triangles"]), W, H, dev(c["background"]))
         out2.backward(dev(c["grad_out"]))
     assert_bits(out2.detach().cpu().numpy(), c["out"], "out")
-    scale = np.abs(c["d_attributes"]).max()
-    assert np.abs(at2.grad.cpu().numpy() - c["d_attributes"]).max() <= 1e-6 + 2e-5 * scale
-    scale = np.abs(c["d_clip_vertices"]).max()
-    assert np.abs(cv2.grad.cpu().numpy() - c["d_clip_vertices"]).max() <= 1e-6 + 2e-5 * scale
+    y = oracle.rasterize_clip_space(c["clip_vertices"], c["attributes"], c["triangles"], W, H, c["background"],
+                                    grad_out=c["grad_out"], f64_yardstick=True)
+    atomic_close(at2.grad.cpu().numpy(), c["d_attributes"], y["d_attributes_f64"], "d_attributes (atomic)")
+    atomic_close(cv2.grad.cpu().numpy(), c["d_clip_vertices"], y["d_vertices_f64"], "d_clip_vertices (atomic)")
 
 
 @pytest.mark.parametrize("name", ["simple_triangle", "perspective_triangle"])
@@ -210,7 +209,7 @@ def test_sphere_views_vs_oracle(pmr, oracle):
     sc = S.sphere_views(40, 39, 3, 160)
     g = S.upstream_gradient((3, 160, 160, 9))
     ref = oracle.rasterize_clip_space(sc["clip_vertices"], sc["attributes"], sc["triangles"], 160, 160,
-                                      sc["background"], grad_out=g)
+                                      sc["background"], grad_out=g, f64_yardstick=True)
     cv = dev(sc["clip_vertices"]).requires_grad_(True)
     at = dev(sc["attributes"]).requires_grad_(True)
     with pmr.backward_mode("ordered"):
@@ -227,8 +226,8 @@ def test_sphere_views_vs_oracle(pmr, oracle):
     at2 = dev(sc["attributes"]).requires_grad_(True)
     with pmr.backward_mode("atomic"):
         pmr.rasterize_clip_space(cv2, at2, dev(sc["triangles"]), 160, 160, dev(sc["background"])).backward(dev(g))
-    assert_close(at2.grad.cpu().numpy(), ref["d_attributes"], "d_attributes (atomic)")
-    assert_close(cv2.grad.cpu().numpy(), ref["d_vertices"], "d_vertices (atomic)")
+    atomic_close(at2.grad.cpu().numpy(), ref["d_attributes"], ref["d_attributes_f64"], "d_attributes (atomic)")
+    atomic_close(cv2.grad.cpu().numpy(), ref["d_vertices"], ref["d_vertices_f64"], "d_vertices (atomic)")
 
 
 def test_occlusion_soup_vs_oracle(pmr, oracle):
