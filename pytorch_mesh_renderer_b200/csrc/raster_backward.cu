@@ -167,6 +167,128 @@ backward_atomic_kernel(const float *__restrict__ grad, const float *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// Atomic mode, warp-aggregated: the throughput path
+// ---------------------------------------------------------------------------------------------
+//
+// One warp owns an 8x4 pixel block (the same shape the forward kernel rasterizes), one lane per
+// pixel.  Every covered lane evaluates its NV = 9 (+3A) per-pixel sums (9 vertex terms, and
+// g_a*alpha*b_k for every corner k and attribute a) and parks them in a shared-memory row.  Lanes
+// are grouped by triangle id with match.any; the warp then walks the (group, column) pairs 32 at
+// a time, each lane adding one column over the lanes of one group, and issues ONE atomic per pair:
+// NV atomics per (block, triangle) instead of per pixel, and the lanes of one instruction hit
+// consecutive words of the same vertex rows, which the memory system merges per 32-byte sector
+// (profiles/microbench/atomics_bench.cu: 3.8x the lane rate of scattered atomics).
+
+template <bool FUSED, int A_STATIC, int kBlockWarps>
+__global__ void __launch_bounds__(kBlockWarps * 32)
+backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__ verts,
+                       const float *__restrict__ attrs, const int32_t *__restrict__ tris,
+                       const int32_t *__restrict__ ids, const float *__restrict__ bary,
+                       int V, int W, int H, int blocks_x, int blocks_per_image, long long n_blocks,
+                       float *__restrict__ d_verts, float *__restrict__ d_attrs) {
+  constexpr int A = A_STATIC;
+  constexpr int NV = 9 + (FUSED ? 3 * A : 0);
+  constexpr int STRIDE = (NV + 3) | 1;           // NV sums + 3 vertex ids, odd => conflict-free rows
+  __shared__ float rows_all[kBlockWarps][32 * STRIDE];
+  __shared__ float stage_all[kBlockWarps][FUSED ? 32 * A : 1];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long blk = (long long)blockIdx.x * kBlockWarps + warp;
+  if (blk >= n_blocks) return;
+  const int b = (int)(blk / blocks_per_image);
+  const int rem = (int)(blk % blocks_per_image);
+  const int x0 = (rem % blocks_x) * 8, y0 = (rem / blocks_x) * 4;
+  const int ix = x0 + (lane & 7), iy = y0 + (lane >> 3);
+  const bool in_image = ix < W && iy < H;
+  const long long p = ((long long)b * H + iy) * W + ix;
+
+  int id = -1;
+  float bp[3] = {0.0f, 0.0f, 0.0f};
+  if (in_image) {
+    id = ids[p];
+    bp[0] = bary[3 * p]; bp[1] = bary[3 * p + 1]; bp[2] = bary[3 * p + 2];
+    if (!pixel_is_covered(id, bp)) id = -1;
+  }
+  const unsigned covered = __ballot_sync(0xffffffffu, id >= 0);
+  if (covered == 0u) return;
+
+  float *rows = rows_all[warp];
+  float g_local[FUSED ? A : 3];
+  if (FUSED) {
+    // Stage the block's gradient rows through shared memory: a block row is 8*A contiguous
+    // floats, read as float4 when the image rows keep them 16-byte aligned.
+    float *stage = stage_all[warp];
+    if ((W & 7) == 0) {
+      constexpr int V4_PER_ROW = 2 * A;          // 8*A floats
+#pragma unroll
+      for (int k = lane; k < 4 * V4_PER_ROW; k += 32) {
+        const int r = k / V4_PER_ROW, c = k % V4_PER_ROW;
+        if (y0 + r < H) {
+          const float4 v = __ldg(reinterpret_cast<const float4 *>(grad + (((long long)b * H + y0 + r) * W + x0) * A) + c);
+          reinterpret_cast<float4 *>(stage + r * 8 * A)[c] = v;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int a = 0; a < A; ++a) g_local[a] = stage[lane * A + a];
+    } else if (in_image) {
+#pragma unroll
+      for (int a = 0; a < A; ++a) g_local[a] = __ldg(grad + p * A + a);
+    }
+  } else if (in_image) {
+    g_local[0] = grad[3 * p]; g_local[1] = grad[3 * p + 1]; g_local[2] = grad[3 * p + 2];
+  }
+
+  if (id >= 0) {
+    PixelGrad pg;
+    const float *verts_b = verts + (size_t)b * V * 4;
+    const float *attrs_b = FUSED ? attrs + (size_t)b * V * A : nullptr;
+    pixel_grad<FUSED>(verts_b, attrs_b, tris, id, bp, g_local, A, pg);
+    float *row = rows + lane * STRIDE;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) row[k] = pg.terms[k];
+    if (FUSED) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int a = 0; a < A; ++a) row[9 + k * A + a] = (g_local[a] * pg.alpha) * pg.b[k];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) row[NV + j] = __int_as_float(pg.vid[j]);
+  }
+  // Group the covered lanes by triangle.  Uncovered lanes get private keys so they match nobody.
+  const unsigned peers = __match_any_sync(0xffffffffu, id >= 0 ? id : -1 - lane);
+  const bool is_leader = id >= 0 && (__ffs(peers) - 1) == lane;
+  const unsigned leaders = __ballot_sync(0xffffffffu, is_leader);
+  const int n_tasks = __popc(leaders) * NV;
+  __syncwarp();
+
+  float *dv = d_verts ? d_verts + (size_t)b * V * 4 : nullptr;
+  float *da = (FUSED && d_attrs) ? d_attrs + (size_t)b * V * A : nullptr;
+  for (int t0 = 0; t0 < n_tasks; t0 += 32) {
+    const int task = t0 + lane;
+    const bool live = task < n_tasks;
+    const int grp = live ? task / NV : 0, c = live ? task % NV : 0;
+    const int leader = __fns(leaders, 0, grp + 1);
+    unsigned members = __shfl_sync(0xffffffffu, peers, leader);
+    if (!live) continue;
+    float acc = 0.0f;
+    while (members) {
+      const int src = __ffs(members) - 1;
+      members &= members - 1;
+      acc += rows[src * STRIDE + c];
+    }
+    const float *lrow = rows + leader * STRIDE;
+    if (c < 9) {
+      if (dv) atomicAdd(dv + (size_t)__float_as_int(lrow[NV + c / 3]) * 4 + column_of(c % 3), acc);
+    } else if (FUSED) {
+      const int k = (c - 9) / A, a = (c - 9) % A;
+      if (da) atomicAdd(da + (size_t)__float_as_int(lrow[NV + k]) * A + a, acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Ordered (parity) mode
 // ---------------------------------------------------------------------------------------------
 
@@ -312,15 +434,23 @@ int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, 
     if (d_verts) PMR_CUDA(ctx, cudaMemsetAsync(d_verts, 0, (size_t)n_pairs * 4 * sizeof(float), stream));
     if (fused && d_attrs) PMR_CUDA(ctx, cudaMemsetAsync(d_attrs, 0, (size_t)n_pairs * A * sizeof(float), stream));
     if (total == 0 || T == 0) return PMR_OK;
-    const unsigned grid = (unsigned)((total + 255) / 256);
-#define PMR_LAUNCH(F, AS)                                                                             \
-  backward_atomic_kernel<F, AS><<<grid, 256, 0, stream>>>(grad, verts, attrs, tris, ids, bary, V, A, ppi, \
-                                                          total, d_verts, d_attrs)
-    if (!fused) PMR_LAUNCH(false, 0);
-    else if (A == 9) PMR_LAUNCH(true, 9);
-    else if (A == 4) PMR_LAUNCH(true, 4);
-    else PMR_LAUNCH(true, 0);
-#undef PMR_LAUNCH
+    const int blocks_x = (W + 7) / 8, blocks_y = (H + 3) / 4;
+    const long long n_blocks = (long long)blocks_x * blocks_y * B;
+#define PMR_BLOCKS(F, AS, WARPS)                                                                          \
+  backward_blocks_kernel<F, AS, WARPS><<<(unsigned)((n_blocks + WARPS - 1) / WARPS), WARPS * 32, 0, stream>>>(       \
+      grad, verts, attrs, tris, ids, bary, V, W, H, blocks_x, blocks_x * blocks_y, n_blocks, d_verts, d_attrs)
+    if (!fused) PMR_BLOCKS(false, 1, 8);
+    else if (A == 9) PMR_BLOCKS(true, 9, 8);
+    else if (A == 4) PMR_BLOCKS(true, 4, 8);
+    else if (A == 12) PMR_BLOCKS(true, 12, 4);
+    else if (A == 13) PMR_BLOCKS(true, 13, 4);
+    else {
+      // other attribute counts: one thread per pixel, per-lane atomics
+      const unsigned grid = (unsigned)((total + 255) / 256);
+      backward_atomic_kernel<true, 0><<<grid, 256, 0, stream>>>(grad, verts, attrs, tris, ids, bary, V, A, ppi, total,
+                                                                d_verts, d_attrs);
+    }
+#undef PMR_BLOCKS
     ctx->launches += 1;
     return check_launch(ctx, "backward_atomic_kernel");
   }

@@ -57,6 +57,7 @@ class BarycentricRasterizer(torch.autograd.Function):
         ctx.batched = batched
         ctx.mode = get_backward_mode()
         ctx.mark_non_differentiable(ids)
+        ctx.set_materialize_grads(False)      # no zero-filled [H,W] gradients for unused outputs
         if not batched:
             ids, bary, z = ids[0], bary[0], z[0]
         return ids, bary, z
@@ -64,6 +65,8 @@ class BarycentricRasterizer(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _, df_dbarycentric_coords, __):
         v, triangles, ids, bary = ctx.saved_tensors
+        if df_dbarycentric_coords is None:
+            return torch.zeros_like(v if ctx.batched else v[0]), torch.zeros_like(triangles), None, None
         g = df_dbarycentric_coords if ctx.batched else df_dbarycentric_coords.unsqueeze(0)
         df_dvertices = ops.rasterize_backward(g, v, triangles, ids, bary, ctx.mode)
         if not ctx.batched:
@@ -83,7 +86,8 @@ class RasterizeInterpolate(torch.autograd.Function):
             clip_space_vertices, attributes, triangles, background_value, image_width, image_height)
         ctx.save_for_backward(clip_space_vertices, attributes, triangles, ids, bary)
         ctx.mode = get_backward_mode()
-        ctx.mark_non_differentiable(ids)
+        ctx.mark_non_differentiable(ids, bary, z)     # the buffers are by-products here
+        ctx.set_materialize_grads(False)
         return image, ids, bary, z
 
     @staticmethod
@@ -91,6 +95,8 @@ class RasterizeInterpolate(torch.autograd.Function):
         v, a, triangles, ids, bary = ctx.saved_tensors
         need_v, need_a, _, _, _, need_bg = ctx.needs_input_grad
         dv = da = d_bg = None
+        if grad_image is None:
+            return None, None, None, None, None, None
         if need_v or need_a:
             dv, da = ops.rasterize_interpolate_backward(grad_image.contiguous(), v, a, triangles, ids, bary,
                                                         ctx.mode, need_vertices=need_v, need_attributes=need_a)
