@@ -259,31 +259,41 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
   // Group the covered lanes by triangle.  Uncovered lanes get private keys so they match nobody.
   const unsigned peers = __match_any_sync(0xffffffffu, id >= 0 ? id : -1 - lane);
   const bool is_leader = id >= 0 && (__ffs(peers) - 1) == lane;
-  const unsigned leaders = __ballot_sync(0xffffffffu, is_leader);
-  const int n_tasks = __popc(leaders) * NV;
+  unsigned leaders = __ballot_sync(0xffffffffu, is_leader);
   __syncwarp();
 
+  // Lane c owns column c (and column c + 32 when NV > 32) of every group.  The walk over groups
+  // and over the lanes of a group is warp-uniform, so only the shared-memory read and the add are
+  // per-lane work.  Column -> (corner, offset in the vertex row) depends on the lane only.
+  const int c0 = lane, c1 = lane + 32;
+  const bool has0 = c0 < NV, has1 = c1 < NV;
+  auto corner_of = [](int c) { return c < 9 ? c / 3 : (c - 9) / (A > 0 ? A : 1); };
+  auto offset_of = [](int c) { return c < 9 ? column_of(c % 3) : (c - 9) % (A > 0 ? A : 1); };
+  const int corner0 = has0 ? corner_of(c0) : 0, corner1 = has1 ? corner_of(c1) : 0;
+  const int off0 = has0 ? offset_of(c0) : 0, off1 = has1 ? offset_of(c1) : 0;
   float *dv = d_verts ? d_verts + (size_t)b * V * 4 : nullptr;
   float *da = (FUSED && d_attrs) ? d_attrs + (size_t)b * V * A : nullptr;
-  for (int t0 = 0; t0 < n_tasks; t0 += 32) {
-    const int task = t0 + lane;
-    const bool live = task < n_tasks;
-    const int grp = live ? task / NV : 0, c = live ? task % NV : 0;
-    const int leader = __fns(leaders, 0, grp + 1);
+  while (leaders) {
+    const int leader = __ffs(leaders) - 1;
+    leaders &= leaders - 1;
     unsigned members = __shfl_sync(0xffffffffu, peers, leader);
-    if (!live) continue;
-    float acc = 0.0f;
+    float acc0 = 0.0f, acc1 = 0.0f;
     while (members) {
       const int src = __ffs(members) - 1;
       members &= members - 1;
-      acc += rows[src * STRIDE + c];
+      const float *row = rows + src * STRIDE;
+      if (has0) acc0 += row[c0];
+      if (NV > 32 && has1) acc1 += row[c1];
     }
     const float *lrow = rows + leader * STRIDE;
-    if (c < 9) {
-      if (dv) atomicAdd(dv + (size_t)__float_as_int(lrow[NV + c / 3]) * 4 + column_of(c % 3), acc);
-    } else if (FUSED) {
-      const int k = (c - 9) / A, a = (c - 9) % A;
-      if (da) atomicAdd(da + (size_t)__float_as_int(lrow[NV + k]) * A + a, acc);
+    if (has0) {
+      const size_t vtx = (size_t)__float_as_int(lrow[NV + corner0]);
+      if (c0 < 9) { if (dv) atomicAdd(dv + vtx * 4 + off0, acc0); }
+      else if (da) atomicAdd(da + vtx * A + off0, acc0);
+    }
+    if (NV > 32 && has1) {
+      const size_t vtx = (size_t)__float_as_int(lrow[NV + corner1]);
+      if (da) atomicAdd(da + vtx * A + off1, acc1);
     }
   }
 }
