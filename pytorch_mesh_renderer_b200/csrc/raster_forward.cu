@@ -3,17 +3,28 @@
 // of rasterize_clip_space (rast.py:118-150) fused into its epilogue.
 //
 // Pipeline per call (all on one stream):
-//   bin_count_kernel   one thread per (image, triangle): pixel box -> tile range, per-tile counts
+//   bin_count_kernel   one thread per (image, triangle): pixel box (kept, 8 bytes) -> per-tile counts
 //   bin_offsets_kernel warp-aggregated allocation of one contiguous list range per tile
 //   bin_fill_kernel    writes triangle ids into the tile lists (order inside a list is arbitrary)
-//   raster_tile_kernel one CTA per 16x16-pixel tile: stages triangle setup records into shared
-//                      memory, every warp culls them against its own 8x4 pixel block with a
-//                      ballot, each lane owns one pixel and keeps its depth-test winner in
-//                      registers (no atomics), then writes ids / barycentrics / z (+ attributes).
+//   raster_tile_kernel one CTA per 16x16-pixel tile.  Triangle setup records (edge equations, z, w,
+//                      pixel box) are staged into shared memory 256 at a time and split by the size
+//                      of their box inside the tile:
+//                        small (<= 64 pixels): the boxes are cut into row segments of up to four
+//                          pixels, the segments of all small triangles are laid out back to back and
+//                          dealt to the 256 threads (balanced work whatever the triangle sizes);
+//                          a thread runs the inside test on its four pixels, the inside pixels of a
+//                          warp are compacted and dealt to its lanes again for barycentrics / depth,
+//                          and depth is resolved with a packed 64-bit atomicMin(depth bits, ~id) on a
+//                          shared-memory key per pixel;
+//                        big: one WARP per 8x4 pixel block culls the records with a ballot and each
+//                          lane tests its own pixel, keeping its winner in registers.
+//                      The per-pixel minimum of both paths is the winner; a winner that came through
+//                      the key buffer is re-evaluated once (same arithmetic, same bits) and ids /
+//                      barycentrics / z (+ interpolated attributes) are written.
 // Meshes with few triangles skip binning: every tile walks the whole triangle array.
 //
-// The depth rule is order independent (min z, then max id -- SURVEY.md F1), so list order
-// does not matter and the result is deterministic.
+// The depth rule is order independent (min z, then max id -- SURVEY.md F1), so neither list order
+// nor atomic order matters and the result is deterministic.
 #include "pmr_internal.cuh"
 #include "raster_math.cuh"
 
@@ -35,24 +46,26 @@ __device__ __forceinline__ void load_triangle(const float *__restrict__ verts_b,
   c = __ldg(v4 + i2);
 }
 
-// Tile range of a pixel box, packed as four uint16 (tx0, tx1, ty0, ty1; exclusive upper ends).
-__device__ __forceinline__ uint2 tile_range_of(const PixelBox &box) {
-  uint2 r;
-  if (box.left >= box.right || box.bottom >= box.top) { r.x = 0u; r.y = 0u; return r; }
-  const unsigned tx0 = (unsigned)box.left >> kTileShiftX, tx1 = ((unsigned)box.right + kTileW - 1) >> kTileShiftX;
-  const unsigned ty0 = (unsigned)box.bottom >> kTileShiftY, ty1 = ((unsigned)box.top + kTileH - 1) >> kTileShiftY;
-  r.x = tx0 | (tx1 << 16);
-  r.y = ty0 | (ty1 << 16);
-  return r;
+// Pixel box packed as four uint16: x = left | right << 16, y = bottom | top << 16 (W, H <= 32768).
+__device__ __forceinline__ uint2 pack_box(const PixelBox &box) {
+  if (box.left >= box.right || box.bottom >= box.top) return make_uint2(0u, 0u);
+  return make_uint2((unsigned)box.left | ((unsigned)box.right << 16),
+                    (unsigned)box.bottom | ((unsigned)box.top << 16));
 }
 
-// Visits every tile of the ranges held by the lanes of a warp.  Ranges of up to
+__device__ __forceinline__ int4 unpack_box(uint2 p) {
+  return make_int4((int)(p.x & 0xffffu), (int)(p.x >> 16), (int)(p.y & 0xffffu), (int)(p.y >> 16));
+}
+
+// Visits every tile touched by the boxes held by the lanes of a warp.  Ranges of up to
 // kSerialTiles tiles are walked by their own lane; larger ones are walked by the whole warp
 // so that one screen-filling triangle does not serialise 16k atomics on a single thread.
 template <typename Visit>
-__device__ __forceinline__ void for_each_tile(uint2 range, int tiles_x, Visit visit) {
-  const int tx0 = range.x & 0xffff, tx1 = range.x >> 16;
-  const int ty0 = range.y & 0xffff, ty1 = range.y >> 16;
+__device__ __forceinline__ void for_each_tile(uint2 packed, int tiles_x, Visit visit) {
+  const int4 box = unpack_box(packed);
+  const bool empty = box.x >= box.y || box.z >= box.w;
+  const int tx0 = box.x >> kTileShiftX, tx1 = empty ? tx0 : (box.y + kTileW - 1) >> kTileShiftX;
+  const int ty0 = box.z >> kTileShiftY, ty1 = empty ? ty0 : (box.w + kTileH - 1) >> kTileShiftY;
   const int nx = tx1 - tx0, n = nx * (ty1 - ty0);
   constexpr int kSerialTiles = 8;
   if (n > 0 && n <= kSerialTiles) {
@@ -76,18 +89,18 @@ __device__ __forceinline__ void for_each_tile(uint2 range, int tiles_x, Visit vi
 __global__ void __launch_bounds__(256)
 bin_count_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris,
                  int V, int T, int W, int H, float half_w, float half_h, int tiles_x, int tiles_per_image,
-                 uint2 *__restrict__ tri_ranges, int *__restrict__ tile_counts) {
+                 uint2 *__restrict__ tri_boxes, int *__restrict__ tile_counts) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint2 range = make_uint2(0u, 0u);
+  uint2 packed = make_uint2(0u, 0u);
   if (t < T) {
     float4 p0, p1, p2;
     load_triangle(verts + (size_t)b * V * 4, tris, t, p0, p1, p2);
-    range = tile_range_of(triangle_box(p0, p1, p2, half_w, half_h, W, H));
-    tri_ranges[(size_t)b * T + t] = range;
+    packed = pack_box(triangle_box(p0, p1, p2, half_w, half_h, W, H));
+    tri_boxes[(size_t)b * T + t] = packed;
   }
   int *counts = tile_counts + (size_t)b * tiles_per_image;
-  for_each_tile(range, tiles_x, [&](int tile, int) { atomicAdd(counts + tile, 1); });
+  for_each_tile(packed, tiles_x, [&](int tile, int) { atomicAdd(counts + tile, 1); });
 }
 
 // One contiguous range per tile; ranges are handed out warp by warp from a global cursor, so
@@ -113,16 +126,16 @@ bin_offsets_kernel(const int *__restrict__ tile_counts, int n_tiles, int *__rest
 }
 
 __global__ void __launch_bounds__(256)
-bin_fill_kernel(const uint2 *__restrict__ tri_ranges, int T, int tiles_x, int tiles_per_image,
+bin_fill_kernel(const uint2 *__restrict__ tri_boxes, int T, int tiles_x, int tiles_per_image,
                 const int *__restrict__ tile_offsets, int *__restrict__ tile_cursors,
                 int32_t *__restrict__ tile_lists) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint2 range = t < T ? tri_ranges[(size_t)b * T + t] : make_uint2(0u, 0u);
+  const uint2 packed = t < T ? tri_boxes[(size_t)b * T + t] : make_uint2(0u, 0u);
   const int *offsets = tile_offsets + (size_t)b * tiles_per_image;
   int *cursors = tile_cursors + (size_t)b * tiles_per_image;
   const int lane = threadIdx.x & 31;
-  for_each_tile(range, tiles_x, [&](int tile, int owner) {
+  for_each_tile(packed, tiles_x, [&](int tile, int owner) {
     const int tri = owner < 0 ? t : (t - lane + owner);
     const int slot = atomicAdd(cursors + tile, 1);
     tile_lists[(size_t)offsets[tile] + slot] = tri;
@@ -133,41 +146,73 @@ bin_fill_kernel(const uint2 *__restrict__ tri_ranges, int T, int tiles_x, int ti
 // Per-tile raster kernel
 // ---------------------------------------------------------------------------------------------
 
-constexpr int kChunk = 256;   // triangles staged per round == threads per CTA
+constexpr int kChunk = 256;                 // triangles staged per round == threads per CTA
+constexpr int kTilePixels = kTileW * kTileH;
+constexpr int kSegCap = 2048;               // row segments of small triangles held per round
+constexpr int kWarps = kChunk / 32;
 
 struct TileSmem {
   // Setup record of one staged triangle, split into float4 planes so that staging stores are
-  // conflict free and the warp-uniform reads in the pixel loop are broadcasts.
+  // conflict free and warp-uniform reads are broadcasts.
   float4 r0[kChunk];   // m0 m1 m2 | id
   float4 r1[kChunk];   // m3 m4 m5 | z0
   float4 r2[kChunk];   // m6 m7 m8 | z1
   float4 r3[kChunk];   // z2 | w0 w1 w2
-  int4 box[kChunk];    // left right bottom top (pixels)
+  int4 box[kChunk];    // the triangle's pixel box: left right bottom top
+  unsigned long long key[kTilePixels];   // packed (depth, ~id) minimum per pixel (small-triangle path)
+  unsigned segs[kSegCap];                // slot | row << 8 | first column << 12 | width << 16
+  unsigned short hits[kWarps][128];      // per warp: inside pixels of its 32 segments (slot << 8 | pixel)
+  unsigned short big_list[kChunk];
+  float cx[kTileW], cy[kTileH];          // pixel-centre NDC coordinates of the tile's columns / rows
+  int warp_sums[kWarps], warp_valid[kWarps];
+  int n_big;
 };
+
+// Appends the slots of the threads with `flag` set to `list` (order irrelevant).
+__device__ __forceinline__ void append_slots(bool flag, unsigned short *list, int *count) {
+  const unsigned votes = __ballot_sync(0xffffffffu, flag);
+  if (votes == 0u) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(count, __popc(votes));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (flag) list[base + __popc(votes & ((1u << lane) - 1u))] = (unsigned short)threadIdx.x;
+}
+
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += up;
+  }
+  return v;
+}
 
 template <int A_STATIC>
 __global__ void __launch_bounds__(kChunk)
 raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris,
-                   int V, int T, int W, int H, float half_w, float half_h, int tiles_x, int tiles_per_image,
+                   int V, int T, int W, int H, float half_w, float half_h, int tiles_per_image,
                    const int *__restrict__ tile_counts, const int *__restrict__ tile_offsets,
-                   const int32_t *__restrict__ tile_lists,
+                   const int32_t *__restrict__ tile_lists, const uint2 *__restrict__ tri_boxes,
                    int32_t *__restrict__ out_ids, float *__restrict__ out_bary, float *__restrict__ out_z,
                    const float *__restrict__ attrs, const float *__restrict__ background, int A_dyn,
                    float *__restrict__ out_image) {
   __shared__ TileSmem sm;
   const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
-  const int b = blockIdx.y;
-  const int tile = blockIdx.x;
-  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const int b = blockIdx.z;
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  const int tile_x0 = blockIdx.x * kTileW, tile_y0 = blockIdx.y * kTileH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 8 warps, each an 8x4 pixel block; blocks are laid out 2 across, 4 down inside the 16x16 tile.
-  const int blk_x0 = tile_x * kTileW + (warp & 1) * 8;
-  const int blk_y0 = tile_y * kTileH + (warp >> 1) * 4;
-  const int ix = blk_x0 + (lane & 7);
-  const int iy = blk_y0 + (lane >> 3);
-  const float px = pixel_center(ix, half_w);
-  const float py = pixel_center(iy, half_h);
+  const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+  const int blk_x0 = tile_x0 + (warp & 1) * 8, blk_y0 = tile_y0 + (warp >> 1) * 4;
+  const int ix = tile_x0 + lx, iy = tile_y0 + ly;
   const float *verts_b = verts + (size_t)b * V * 4;
+
+  sm.key[threadIdx.x] = kEmptyKey;
+  if (threadIdx.x < kTileW) sm.cx[threadIdx.x] = pixel_center(tile_x0 + threadIdx.x, half_w);
+  else if (threadIdx.x < kTileW + kTileH) sm.cy[threadIdx.x - kTileW] = pixel_center(tile_y0 + threadIdx.x - kTileW, half_h);
 
   int n_list;
   const int32_t *list = nullptr;
@@ -181,35 +226,79 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
 
   Fragment best;
   fragment_clear(best);
+  float px = 0.0f, py = 0.0f;
 
   for (int base = 0; base < n_list; base += kChunk) {
     const int n_here = min(kChunk, n_list - base);
-    __syncthreads();       // previous chunk fully consumed
+    __syncthreads();       // previous chunk fully consumed (also publishes cx / cy / key)
+    if (threadIdx.x == 0) sm.n_big = 0;
+    if (base == 0) { px = sm.cx[lx]; py = sm.cy[ly]; }
+
+    // ---- stage: thread i sets up triangle i of the chunk
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0, n_seg = 0;
+    bool overlaps = false;
     if (threadIdx.x < n_here) {
       const int t = list ? list[base + threadIdx.x] : base + threadIdx.x;
       float4 p0, p1, p2;
       load_triangle(verts_b, tris, t, p0, p1, p2);
-      const PixelBox bx = triangle_box(p0, p1, p2, half_w, half_h, W, H);
+      int4 bx;
+      if (tri_boxes != nullptr) {
+        bx = unpack_box(__ldg(tri_boxes + (size_t)b * T + t));
+      } else {
+        const PixelBox pb = triangle_box(p0, p1, p2, half_w, half_h, W, H);
+        bx = make_int4(pb.left, pb.right, pb.bottom, pb.top);
+      }
       float m[9];
       adjugate_signed(p0.x, p1.x, p2.x, p0.y, p1.y, p2.y, p0.w, p1.w, p2.w, m);
       sm.r0[threadIdx.x] = make_float4(m[0], m[1], m[2], __int_as_float(t));
       sm.r1[threadIdx.x] = make_float4(m[3], m[4], m[5], p0.z);
       sm.r2[threadIdx.x] = make_float4(m[6], m[7], m[8], p1.z);
       sm.r3[threadIdx.x] = make_float4(p2.z, p0.w, p1.w, p2.w);
-      sm.box[threadIdx.x] = make_int4(bx.left, bx.right, bx.bottom, bx.top);
+      sm.box[threadIdx.x] = bx;
+      // the box inside this tile, in tile-local pixel coordinates
+      x0 = max(bx.x, tile_x0) - tile_x0; x1 = min(bx.y, tile_x0 + kTileW) - tile_x0;
+      y0 = max(bx.z, tile_y0) - tile_y0; y1 = min(bx.w, tile_y0 + kTileH) - tile_y0;
+      overlaps = x1 > x0 && y1 > y0;
+      if (overlaps && (x1 - x0) * (y1 - y0) <= 64) n_seg = (y1 - y0) * ((x1 - x0 + 3) >> 2);
     }
+    // ---- lay the row segments of the small triangles out back to back (block-wide exclusive scan)
+    const int incl = warp_inclusive_scan(n_seg);
+    if (lane == 31) sm.warp_sums[warp] = incl;
     __syncthreads();
+    int seg_begin = incl - n_seg;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv)
+      if (wv < warp) seg_begin += sm.warp_sums[wv];
+    // Triangles whose segments do not fit the buffer (and all large ones) take the big path.  The
+    // scan is monotone in thread order, so the segments that do fit form a prefix of the buffer.
+    const bool small = n_seg > 0 && seg_begin + n_seg <= kSegCap;
+    if (small) {
+      int k = seg_begin;
+      for (int yy = y0; yy < y1; ++yy)
+        for (int xs = x0; xs < x1; xs += 4)
+          sm.segs[k++] = threadIdx.x | (yy << 8) | (xs << 12) | (min(4, x1 - xs) << 16);
+    }
+    append_slots(overlaps && !small, sm.big_list, &sm.n_big);
+    int valid = small ? seg_begin + n_seg : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) valid = max(valid, __shfl_xor_sync(0xffffffffu, valid, d));
+    if (lane == 0) sm.warp_valid[warp] = valid;
+    __syncthreads();
+    const int n_big = sm.n_big;
+    int total_segs = 0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) total_segs = max(total_segs, sm.warp_valid[wv]);
 
-    for (int g0 = 0; g0 < n_here; g0 += 32) {
-      // Coarse: lane j holds triangle g0+j; does its pixel box touch this warp's 8x4 block?
+    // ---- big triangles: warp per 8x4 block, ballot cull, lane per pixel
+    for (int g0 = 0; g0 < n_big; g0 += 32) {
       bool touches = false;
-      if (g0 + lane < n_here) {
-        const int4 bx = sm.box[g0 + lane];
+      if (g0 + lane < n_big) {
+        const int4 bx = sm.box[sm.big_list[g0 + lane]];
         touches = bx.x < blk_x0 + 8 && bx.y > blk_x0 && bx.z < blk_y0 + 4 && bx.w > blk_y0;
       }
       unsigned todo = __ballot_sync(0xffffffffu, touches);
       while (todo) {
-        const int j = g0 + __ffs(todo) - 1;
+        const int j = sm.big_list[g0 + __ffs(todo) - 1];
         todo &= todo - 1;
         const int4 bx = sm.box[j];
         // The reference only visits pixels inside the triangle's own box (K.cpp:374-375).
@@ -222,9 +311,76 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
         }
       }
     }
+
+    // ---- small triangles: 32 row segments per warp per round
+    unsigned short *hits = sm.hits[warp];
+    for (int s0 = warp * 32; s0 < total_segs; s0 += kChunk) {
+      // pass 1: inside test on the (up to) four pixels of this lane's segment
+      int j = 0, yy = 0, xs = 0;
+      unsigned inside = 0u;
+      if (s0 + lane < total_segs) {
+        const unsigned seg = sm.segs[s0 + lane];
+        j = seg & 0xffu; yy = (seg >> 8) & 0xfu; xs = (seg >> 12) & 0xfu;
+        const int width = seg >> 16;
+        const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j];
+        const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
+        const float cyv = sm.cy[yy];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float e[3], esum;
+          edge_values(m, sm.cx[(xs + k) & (kTileW - 1)], cyv, e);
+          if (edges_inside(e, esum) && k < width) inside |= 1u << k;
+        }
+      }
+      // compact the inside pixels of the warp and deal them to the lanes again
+      const int mine = __popc(inside);
+      const int upto = warp_inclusive_scan(mine);
+      const int n_hits = __shfl_sync(0xffffffffu, upto, 31);
+      int at = upto - mine;
+      while (inside) {
+        const int k = __ffs(inside) - 1;
+        inside &= inside - 1;
+        hits[at++] = (unsigned short)((j << 8) | (yy * kTileW + xs + k));
+      }
+      __syncwarp();
+      // pass 2: barycentrics / depth for exactly those pixels, depth resolve by packed atomicMin
+      for (int h = lane; h < n_hits; h += 32) {
+        const unsigned hit = hits[h];
+        const int jj = hit >> 8, pix = hit & 0xffu;
+        const float4 q0 = sm.r0[jj], q1 = sm.r1[jj], q2 = sm.r2[jj], q3 = sm.r3[jj];
+        const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
+        const float zc[3] = {q1.w, q2.w, q3.x};
+        const float wc[3] = {q3.y, q3.z, q3.w};
+        float e[3], esum, bc[3], z;
+        edge_values(m, sm.cx[pix & (kTileW - 1)], sm.cy[pix >> kTileShiftX], e);
+        edges_inside(e, esum);
+        if (fragment_depth(e, esum, zc, wc, bc, z))
+          atomicMin(&sm.key[pix], depth_key(z, __float_as_int(q0.w)));
+      }
+      __syncwarp();
+    }
   }
+  __syncthreads();
 
   if (ix >= W || iy >= H) return;
+  if (n_list == 0) { px = pixel_center(ix, half_w); py = pixel_center(iy, half_h); }
+
+  // ---- resolve: minimum of the two paths; re-evaluate the winner if it came from the key buffer
+  const unsigned long long key_small = sm.key[ly * kTileW + lx];
+  const unsigned long long key_big = best.id >= 0 ? depth_key(best.z, best.id) : kEmptyKey;
+  if (key_small < key_big) {
+    const int t = depth_key_id(key_small);
+    float4 p0, p1, p2;
+    load_triangle(verts_b, tris, t, p0, p1, p2);
+    float m[9], e[3], esum, bc[3], z;
+    adjugate_signed(p0.x, p1.x, p2.x, p0.y, p1.y, p2.y, p0.w, p1.w, p2.w, m);
+    edge_values(m, px, py, e);
+    edges_inside(e, esum);
+    const float zc[3] = {p0.z, p1.z, p2.z}, wc[3] = {p0.w, p1.w, p2.w};
+    fragment_depth(e, esum, zc, wc, bc, z);
+    best.z = z; best.id = t; best.b0 = bc[0]; best.b1 = bc[1]; best.b2 = bc[2];
+  }
+
   const size_t p = ((size_t)b * H + iy) * W + ix;
   const bool covered = best.id >= 0;
   const int id = covered ? best.id : 0;
@@ -285,16 +441,16 @@ interpolate_kernel(const float *__restrict__ attrs, const int32_t *__restrict__ 
 
 static int launch_raster(Context *ctx, const float *verts, const int32_t *tris, int B, int V, int T,
                          int W, int H, const int *counts, const int *offsets, const int32_t *lists,
-                         int32_t *ids, float *bary, float *z, const float *attrs, const float *bg, int A,
+                         const uint2 *boxes, int32_t *ids, float *bary, float *z, const float *attrs, const float *bg, int A,
                          float *image, cudaStream_t stream) {
   const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
   const int tiles = tiles_x * tiles_y;
   const float half_w = (float)(0.5 * W), half_h = (float)(0.5 * H);   // K.cpp:309-310
-  dim3 grid(tiles, B);
+  dim3 grid(tiles_x, tiles_y, B);
   StageScope timed(ctx, PMR_STAGE_RASTER, stream);
 #define PMR_LAUNCH(AS)                                                                              \
   raster_tile_kernel<AS><<<grid, kChunk, 0, stream>>>(verts, tris, V, T, W, H, half_w, half_h,      \
-                                                     tiles_x, tiles, counts, offsets, lists, ids,   \
+                                                     tiles, counts, offsets, lists, boxes, ids,     \
                                                      bary, z, attrs, bg, A, image)
   if (image == nullptr) PMR_LAUNCH(0);
   else if (A == 4) PMR_LAUNCH(4);
@@ -316,13 +472,14 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
   const float half_w = (float)(0.5 * W), half_h = (float)(0.5 * H);
 
   if (T <= ctx->small_mesh_threshold) {
-    return launch_raster(ctx, verts, tris, B, V, T, W, H, nullptr, nullptr, nullptr, ids, bary, z, attrs,
+    return launch_raster(ctx, verts, tris, B, V, T, W, H, nullptr, nullptr, nullptr, nullptr, ids, bary, z, attrs,
                          bg, A, image, stream);
   }
 
   const size_t n_tiles = (size_t)B * tiles;
   int32_t *lists = nullptr;
   int *counts = nullptr, *offsets = nullptr;
+  uint2 *ranges = nullptr;      // packed pixel box per (image, triangle)
   {
   StageScope timed(ctx, PMR_STAGE_BIN, stream);
   if (n_tiles > (size_t)INT_MAX) return set_error(ctx, PMR_ERR_SIZE, "too many screen tiles");
@@ -334,7 +491,7 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
   counts = (int *)(base + 16);
   int *cursors = counts + n_tiles;
   offsets = cursors + n_tiles;
-  uint2 *ranges = (uint2 *)(((uintptr_t)(offsets + n_tiles) + 15) & ~(uintptr_t)15);
+  ranges = (uint2 *)(((uintptr_t)(offsets + n_tiles) + 15) & ~(uintptr_t)15);
 
   PMR_CUDA(ctx, cudaMemsetAsync(base, 0, 16 + n_tiles * 2 * sizeof(int), stream));
   dim3 tgrid((T + 255) / 256, B);
@@ -362,7 +519,7 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
   rc = check_launch(ctx, "bin_fill_kernel");
   if (rc) return rc;
   }
-  return launch_raster(ctx, verts, tris, B, V, T, W, H, counts, offsets, lists, ids, bary, z, attrs, bg, A,
+  return launch_raster(ctx, verts, tris, B, V, T, W, H, counts, offsets, lists, ranges, ids, bary, z, attrs, bg, A,
                        image, stream);
 }
 
