@@ -148,8 +148,8 @@ bin_fill_kernel(const uint2 *__restrict__ tri_boxes, int T, int tiles_x, int til
 
 constexpr int kChunk = 256;                 // triangles staged per round == threads per CTA
 constexpr int kTilePixels = kTileW * kTileH;
-constexpr int kSegCap = 2048;               // row segments of small triangles held per round
 constexpr int kWarps = kChunk / 32;
+constexpr int kWarpSegCap = 256;            // row segments of small triangles a warp holds per round
 
 struct TileSmem {
   // Setup record of one staged triangle, split into float4 planes so that staging stores are
@@ -160,13 +160,16 @@ struct TileSmem {
   float4 r3[kChunk];   // z2 | w0 w1 w2
   int4 box[kChunk];    // the triangle's pixel box: left right bottom top
   unsigned long long key[kTilePixels];   // packed (depth, ~id) minimum per pixel (small-triangle path)
-  unsigned segs[kSegCap];                // slot | row << 8 | first column << 12 | width << 16
-  unsigned short hits[kWarps][128];      // per warp: inside pixels of its 32 segments (slot << 8 | pixel)
+  unsigned segs[kWarps][kWarpSegCap];    // per warp: slot | row << 8 | first column << 12 | width << 16
+  unsigned short hits[kWarps][128];      // per warp: inside pixels of 32 segments (slot << 8 | pixel)
   unsigned short big_list[kChunk];
   float cx[kTileW], cy[kTileH];          // pixel-centre NDC coordinates of the tile's columns / rows
-  int warp_sums[kWarps], warp_valid[kWarps];
   int n_big;
 };
+
+// After the raster loop the record planes are dead; the epilogue reuses them to transpose each warp's
+// 8x4 pixel block into row-contiguous runs so that global stores are full 16-byte vectors.
+static_assert(sizeof(float4) * kChunk * 4 >= sizeof(float) * kWarps * 32 * 16, "epilogue staging must fit");
 
 // Appends the slots of the threads with `flag` set to `list` (order irrelevant).
 __device__ __forceinline__ void append_slots(bool flag, unsigned short *list, int *count) {
@@ -189,6 +192,33 @@ __device__ __forceinline__ int warp_inclusive_scan(int v) {
   return v;
 }
 
+// Writes N floats per pixel of the warp's 8x4 block from the shared staging area (`stage`: 4 rows x
+// 8*N contiguous floats) to `dst_row0` (+ row * row_stride floats).  The vector path needs 16-byte
+// aligned rows and a full-width block; otherwise scalars.  N is a compile-time constant so that the
+// row/column split is a multiply-shift, not a division.
+template <int N>
+__device__ __forceinline__ void store_block_rows(const float *stage, float *dst_row0, size_t row_stride,
+                                                 int cols, int rows, bool vec_ok) {
+  const int lane = threadIdx.x & 31;
+  constexpr int run = 8 * N;                           // floats per full block row
+  if (vec_ok && cols == 8) {
+    constexpr int v4_per_row = 2 * N;
+#pragma unroll
+    for (int k0 = 0; k0 < 4 * v4_per_row; k0 += 32) {
+      const int k = k0 + lane;
+      const int r = k / v4_per_row, c = k % v4_per_row;
+      if (k < 4 * v4_per_row && r < rows)
+        reinterpret_cast<float4 *>(dst_row0 + r * row_stride)[c] = reinterpret_cast<const float4 *>(stage + r * run)[c];
+    }
+  } else {
+    const int live = cols * N;
+    for (int k = lane; k < rows * run; k += 32) {
+      const int r = k / run, c = k % run;
+      if (c < live) dst_row0[r * row_stride + c] = stage[r * run + c];
+    }
+  }
+}
+
 template <int A_STATIC>
 __global__ void __launch_bounds__(kChunk)
 raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris,
@@ -198,7 +228,7 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
                    int32_t *__restrict__ out_ids, float *__restrict__ out_bary, float *__restrict__ out_z,
                    const float *__restrict__ attrs, const float *__restrict__ background, int A_dyn,
                    float *__restrict__ out_image) {
-  __shared__ TileSmem sm;
+  __shared__ __align__(16) TileSmem sm;
   const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
   const int b = blockIdx.z;
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
@@ -213,6 +243,7 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
   sm.key[threadIdx.x] = kEmptyKey;
   if (threadIdx.x < kTileW) sm.cx[threadIdx.x] = pixel_center(tile_x0 + threadIdx.x, half_w);
   else if (threadIdx.x < kTileW + kTileH) sm.cy[threadIdx.x - kTileW] = pixel_center(tile_y0 + threadIdx.x - kTileW, half_h);
+  if (threadIdx.x == 0) sm.n_big = 0;
 
   int n_list;
   const int32_t *list = nullptr;
@@ -226,19 +257,24 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
 
   Fragment best;
   fragment_clear(best);
-  float px = 0.0f, py = 0.0f;
+  __syncthreads();         // publishes key / cx / cy / n_big
+  const float px = sm.cx[lx], py = sm.cy[ly];
 
   for (int base = 0; base < n_list; base += kChunk) {
     const int n_here = min(kChunk, n_list - base);
-    __syncthreads();       // previous chunk fully consumed (also publishes cx / cy / key)
-    if (threadIdx.x == 0) sm.n_big = 0;
-    if (base == 0) { px = sm.cx[lx]; py = sm.cy[ly]; }
+    if (base > 0) {
+      __syncthreads();     // previous chunk's records fully consumed
+      if (threadIdx.x == 0) sm.n_big = 0;
+      __syncthreads();
+    }
 
-    // ---- stage: thread i sets up triangle i of the chunk
+    // ---- stage: the chunk's triangles are dealt round-robin to the warps (entry lane*8 + warp goes
+    // to this thread) so that every warp owns a similar share of the small-triangle work.
+    const int entry = lane * kWarps + warp;
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0, n_seg = 0;
     bool overlaps = false;
-    if (threadIdx.x < n_here) {
-      const int t = list ? list[base + threadIdx.x] : base + threadIdx.x;
+    if (entry < n_here) {
+      const int t = list ? list[base + entry] : base + entry;
       float4 p0, p1, p2;
       load_triangle(verts_b, tris, t, p0, p1, p2);
       int4 bx;
@@ -261,65 +297,36 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
       overlaps = x1 > x0 && y1 > y0;
       if (overlaps && (x1 - x0) * (y1 - y0) <= 64) n_seg = (y1 - y0) * ((x1 - x0 + 3) >> 2);
     }
-    // ---- lay the row segments of the small triangles out back to back (block-wide exclusive scan)
-    const int incl = warp_inclusive_scan(n_seg);
-    if (lane == 31) sm.warp_sums[warp] = incl;
-    __syncthreads();
-    int seg_begin = incl - n_seg;
-#pragma unroll
-    for (int wv = 0; wv < kWarps; ++wv)
-      if (wv < warp) seg_begin += sm.warp_sums[wv];
-    // Triangles whose segments do not fit the buffer (and all large ones) take the big path.  The
-    // scan is monotone in thread order, so the segments that do fit form a prefix of the buffer.
-    const bool small = n_seg > 0 && seg_begin + n_seg <= kSegCap;
+    // ---- the warp lays the row segments of ITS small triangles out back to back (warp scan).
+    // Triangles whose segments do not fit the warp's buffer, and all large ones, take the big path.
+    const int seg_end = warp_inclusive_scan(n_seg);
+    const bool small = n_seg > 0 && seg_end <= kWarpSegCap;
+    unsigned *segs = sm.segs[warp];
     if (small) {
-      int k = seg_begin;
-      for (int yy = y0; yy < y1; ++yy)
-        for (int xs = x0; xs < x1; xs += 4)
-          sm.segs[k++] = threadIdx.x | (yy << 8) | (xs << 12) | (min(4, x1 - xs) << 16);
+      int k = seg_end - n_seg;
+      const int per_row = (x1 - x0 + 3) >> 2;          // 1..4 segments per row
+      for (int yy = y0; yy < y1; ++yy) {
+        const unsigned head = threadIdx.x | (yy << 8);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < per_row) segs[k + q] = head | ((x0 + 4 * q) << 12) | (min(4, x1 - x0 - 4 * q) << 16);
+        k += per_row;
+      }
     }
+    int total_segs = small ? seg_end : 0;              // the fitting segments form a prefix
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) total_segs = max(total_segs, __shfl_xor_sync(0xffffffffu, total_segs, d));
     append_slots(overlaps && !small, sm.big_list, &sm.n_big);
-    int valid = small ? seg_begin + n_seg : 0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) valid = max(valid, __shfl_xor_sync(0xffffffffu, valid, d));
-    if (lane == 0) sm.warp_valid[warp] = valid;
-    __syncthreads();
-    const int n_big = sm.n_big;
-    int total_segs = 0;
-#pragma unroll
-    for (int wv = 0; wv < kWarps; ++wv) total_segs = max(total_segs, sm.warp_valid[wv]);
+    __syncwarp();
 
-    // ---- big triangles: warp per 8x4 block, ballot cull, lane per pixel
-    for (int g0 = 0; g0 < n_big; g0 += 32) {
-      bool touches = false;
-      if (g0 + lane < n_big) {
-        const int4 bx = sm.box[sm.big_list[g0 + lane]];
-        touches = bx.x < blk_x0 + 8 && bx.y > blk_x0 && bx.z < blk_y0 + 4 && bx.w > blk_y0;
-      }
-      unsigned todo = __ballot_sync(0xffffffffu, touches);
-      while (todo) {
-        const int j = sm.big_list[g0 + __ffs(todo) - 1];
-        todo &= todo - 1;
-        const int4 bx = sm.box[j];
-        // The reference only visits pixels inside the triangle's own box (K.cpp:374-375).
-        if (ix >= bx.x && ix < bx.y && iy >= bx.z && iy < bx.w) {
-          const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j], q3 = sm.r3[j];
-          const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
-          const float zc[3] = {q1.w, q2.w, q3.x};
-          const float wc[3] = {q3.y, q3.z, q3.w};
-          fragment_test(m, zc, wc, px, py, __float_as_int(q0.w), best);
-        }
-      }
-    }
-
-    // ---- small triangles: 32 row segments per warp per round
+    // ---- small triangles (warp-local: no block barrier): 32 row segments per round
     unsigned short *hits = sm.hits[warp];
-    for (int s0 = warp * 32; s0 < total_segs; s0 += kChunk) {
+    for (int s0 = 0; s0 < total_segs; s0 += 32) {
       // pass 1: inside test on the (up to) four pixels of this lane's segment
       int j = 0, yy = 0, xs = 0;
       unsigned inside = 0u;
       if (s0 + lane < total_segs) {
-        const unsigned seg = sm.segs[s0 + lane];
+        const unsigned seg = segs[s0 + lane];
         j = seg & 0xffu; yy = (seg >> 8) & 0xfu; xs = (seg >> 12) & 0xfu;
         const int width = seg >> 16;
         const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j];
@@ -359,11 +366,33 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
       }
       __syncwarp();
     }
-  }
-  __syncthreads();
 
-  if (ix >= W || iy >= H) return;
-  if (n_list == 0) { px = pixel_center(ix, half_w); py = pixel_center(iy, half_h); }
+    // ---- big triangles: warp per 8x4 block, ballot cull, lane per pixel (needs everyone's records)
+    __syncthreads();
+    const int n_big = sm.n_big;
+    for (int g0 = 0; g0 < n_big; g0 += 32) {
+      bool touches = false;
+      if (g0 + lane < n_big) {
+        const int4 bx = sm.box[sm.big_list[g0 + lane]];
+        touches = bx.x < blk_x0 + 8 && bx.y > blk_x0 && bx.z < blk_y0 + 4 && bx.w > blk_y0;
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, touches);
+      while (todo) {
+        const int j = sm.big_list[g0 + __ffs(todo) - 1];
+        todo &= todo - 1;
+        const int4 bx = sm.box[j];
+        // The reference only visits pixels inside the triangle's own box (K.cpp:374-375).
+        if (ix >= bx.x && ix < bx.y && iy >= bx.z && iy < bx.w) {
+          const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j], q3 = sm.r3[j];
+          const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
+          const float zc[3] = {q1.w, q2.w, q3.x};
+          const float wc[3] = {q3.y, q3.z, q3.w};
+          fragment_test(m, zc, wc, px, py, __float_as_int(q0.w), best);
+        }
+      }
+    }
+  }
+  __syncthreads();           // all keys final; record planes dead from here on
 
   // ---- resolve: minimum of the two paths; re-evaluate the winner if it came from the key buffer
   const unsigned long long key_small = sm.key[ly * kTileW + lx];
@@ -380,33 +409,55 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
     fragment_depth(e, esum, zc, wc, bc, z);
     best.z = z; best.id = t; best.b0 = bc[0]; best.b1 = bc[1]; best.b2 = bc[2];
   }
-
-  const size_t p = ((size_t)b * H + iy) * W + ix;
   const bool covered = best.id >= 0;
   const int id = covered ? best.id : 0;
-  out_ids[p] = id;
-  out_z[p] = best.z;
-  out_bary[3 * p + 0] = best.b0;
-  out_bary[3 * p + 1] = best.b1;
-  out_bary[3 * p + 2] = best.b2;
+
+  // ---- epilogue: transpose the warp's block through shared memory, store whole 16-byte vectors
+  float *stage = reinterpret_cast<float *>(sm.r0) + warp * (32 * 16);
+  const int cols = min(8, W - blk_x0), rows = min(4, H - blk_y0);     // <= 0: block outside the image
+  if (cols <= 0 || rows <= 0) return;
+  const bool vec_ok = (W & 3) == 0 &&
+      (((uintptr_t)out_ids | (uintptr_t)out_z | (uintptr_t)out_bary | (uintptr_t)out_image) & 15) == 0;
+  const size_t p0 = ((size_t)b * H + blk_y0) * W + blk_x0;            // first pixel of the block
+  // ids (as raw bits), z, barycentrics
+  stage[lane] = __int_as_float(id);
+  stage[32 + lane] = best.z;
+  stage[64 + 3 * lane + 0] = best.b0;
+  stage[64 + 3 * lane + 1] = best.b1;
+  stage[64 + 3 * lane + 2] = best.b2;
+  __syncwarp();
+  store_block_rows<1>(stage, reinterpret_cast<float *>(out_ids) + p0, (size_t)W, cols, rows, vec_ok);
+  store_block_rows<1>(stage + 32, out_z + p0, (size_t)W, cols, rows, vec_ok);
+  store_block_rows<3>(stage + 64, out_bary + 3 * p0, (size_t)W * 3, cols, rows, vec_ok);
+  __syncwarp();
 
   if (out_image != nullptr) {
     // rast.py:118-150: corner attributes weighted by barycentrics, alpha, background blend.
-    float *o = out_image + p * A;
-    if (!covered) {
-      for (int a = 0; a < A; ++a) o[a] = __ldg(background + a);
-    } else {
-      const float *at = attrs + (size_t)b * V * A;
-      const float *c0 = at + (size_t)__ldg(tris + 3 * (size_t)id + 0) * A;
-      const float *c1 = at + (size_t)__ldg(tris + 3 * (size_t)id + 1) * A;
-      const float *c2 = at + (size_t)__ldg(tris + 3 * (size_t)id + 2) * A;
-      const float alpha = coverage_alpha(best.b0, best.b1, best.b2);
-      const float one_minus = 1.0f - alpha;
+    float *o = stage + lane * A;                      // compiled-in attribute counts go through the staging area
+    const bool staged = A_STATIC > 0 && A_STATIC <= 16;
+    float *direct = out_image + (p0 + (size_t)(lane >> 3) * W + (lane & 7)) * A;
+    float *dst = staged ? o : direct;
+    const bool in_image = (lane & 7) < cols && (lane >> 3) < rows;
+    if (staged || in_image) {
+      if (!covered) {
+        for (int a = 0; a < A; ++a) dst[a] = __ldg(background + a);
+      } else {
+        const float *at = attrs + (size_t)b * V * A;
+        const float *c0 = at + (size_t)__ldg(tris + 3 * (size_t)id + 0) * A;
+        const float *c1 = at + (size_t)__ldg(tris + 3 * (size_t)id + 1) * A;
+        const float *c2 = at + (size_t)__ldg(tris + 3 * (size_t)id + 2) * A;
+        const float alpha = coverage_alpha(best.b0, best.b1, best.b2);
+        const float one_minus = 1.0f - alpha;
 #pragma unroll
-      for (int a = 0; a < A; ++a) {
-        const float img = __ldg(c0 + a) * best.b0 + __ldg(c1 + a) * best.b1 + __ldg(c2 + a) * best.b2;
-        o[a] = alpha * img + one_minus * __ldg(background + a);
+        for (int a = 0; a < A; ++a) {
+          const float img = __ldg(c0 + a) * best.b0 + __ldg(c1 + a) * best.b1 + __ldg(c2 + a) * best.b2;
+          dst[a] = alpha * img + one_minus * __ldg(background + a);
+        }
       }
+    }
+    if (staged) {
+      __syncwarp();
+      store_block_rows<(A_STATIC > 0 ? A_STATIC : 1)>(stage, out_image + p0 * A, (size_t)W * A, cols, rows, vec_ok);
     }
   }
 }
