@@ -184,28 +184,42 @@ def main():
         dist.init_process_group("nccl", device_id=device)
 
     sc = make_workload(args.config, args.batch)
+    shared_mesh = world > 1 and "world_vertices" in sc and sc["world_vertices"].ndim == 2
+    if shared_mesh:
+        # Weak scaling: the job renders world * B views of ONE mesh; this rank owns a contiguous slice.
+        from pytorch_mesh_renderer_b200 import distributed as D
+        from pytorch_mesh_renderer_b200 import synthetic as S
+        from pytorch_mesh_renderer_b200.camera_utils import transform_homogeneous
+        B_local = sc["clip_vertices"].shape[0]
+        mine = D.shard_views(B_local * world, rank, world)
+        sc["camera_matrices"] = S.orbit_cameras(B_local * world)[mine.start:mine.stop]
+        sc["clip_vertices"] = S.transform(sc["camera_matrices"], sc["world_vertices"])
     B, V = sc["clip_vertices"].shape[:2]
     T = sc["triangles"].shape[0]
     H, W = sc["height"], sc["width"]
     P = B * H * W
-    g_host = np.random.default_rng(1).standard_normal((B, H, W, A), dtype=np.float32)
+    g_host = np.random.default_rng(1 + rank).standard_normal((B, H, W, A), dtype=np.float32)
     to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     clip, attrs, tris, bg = (to_dev(sc[k]) for k in ("clip_vertices", "attributes", "triangles", "background"))
     grad = to_dev(g_host)
-    shared_mesh = world > 1
-    mvp = to_dev(sc["camera_matrices"]) if shared_mesh and "camera_matrices" in sc else None
+    if shared_mesh:
+        mvp = to_dev(sc["camera_matrices"])
+        world_vertices = to_dev(sc["world_vertices"])
 
     def step():
-        cv = clip.detach().requires_grad_(True)
         at = attrs.detach().requires_grad_(True)
+        if shared_mesh:
+            # multi-view fitting: the world-space mesh is the shared parameter; d(clip) flows back
+            # through the view matrices and the broadcast, then ONE all-reduce of [V,3] over NVLink.
+            wv = world_vertices.detach().requires_grad_(True)
+            cv = transform_homogeneous(mvp, wv.unsqueeze(0).expand(B, -1, -1))
+            out = pmr.rasterize_clip_space(cv, at, tris, W, H, bg)
+            out.backward(grad)
+            D.all_reduce_gradients([wv.grad])
+            return wv.grad
+        cv = clip.detach().requires_grad_(True)
         out = pmr.rasterize_clip_space(cv, at, tris, W, H, bg)
         out.backward(grad)
-        if mvp is not None:
-            # multi-view fitting: d(clip) -> d(world) through the view matrices, summed over the local
-            # views, then one all-reduce of [V,3] over NVLink.
-            d_world = torch.einsum("bvj,bjk->vk", cv.grad, mvp[:, :, :3])
-            dist.all_reduce(d_world)
-            return d_world
         return cv.grad
 
     with pmr.backward_mode(args.mode):

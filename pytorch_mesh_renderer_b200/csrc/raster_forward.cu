@@ -220,7 +220,7 @@ __device__ __forceinline__ void store_block_rows(const float *stage, float *dst_
 }
 
 template <int A_STATIC>
-__global__ void __launch_bounds__(kChunk)
+__global__ void __launch_bounds__(kChunk, 5)
 raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris,
                    int V, int T, int W, int H, float half_w, float half_h, int tiles_per_image,
                    const int *__restrict__ tile_counts, const int *__restrict__ tile_offsets,
