@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kBlockWarps * 32)
 backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__ verts,
                        const float *__restrict__ attrs, const int32_t *__restrict__ tris,
                        const int32_t *__restrict__ ids, const float *__restrict__ bary,
-                       int V, int W, int H, int blocks_x, int blocks_per_image, long long n_blocks,
+                       int V, int W, int H, int blocks_x, int blocks_per_image,
                        float *__restrict__ d_verts, float *__restrict__ d_attrs) {
   constexpr int A = A_STATIC;
   constexpr int NV = 9 + (FUSED ? 3 * A : 0);
@@ -193,11 +193,11 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
   __shared__ float stage_all[kBlockWarps][FUSED ? 32 * A : 1];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long blk = (long long)blockIdx.x * kBlockWarps + warp;
-  if (blk >= n_blocks) return;
-  const int b = (int)(blk / blocks_per_image);
-  const int rem = (int)(blk % blocks_per_image);
-  const int x0 = (rem % blocks_x) * 8, y0 = (rem / blocks_x) * 4;
+  const int rem = blockIdx.x * kBlockWarps + warp;        // 8x4 block within the image
+  if (rem >= blocks_per_image) return;
+  const int b = blockIdx.y;
+  const int by = rem / blocks_x;
+  const int x0 = (rem - by * blocks_x) * 8, y0 = by * 4;
   const int ix = x0 + (lane & 7), iy = y0 + (lane >> 3);
   const bool in_image = ix < W && iy < H;
   const long long p = ((long long)b * H + iy) * W + ix;
@@ -278,12 +278,19 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
     leaders &= leaders - 1;
     unsigned members = __shfl_sync(0xffffffffu, peers, leader);
     float acc0 = 0.0f, acc1 = 0.0f;
-    while (members) {
+    while (members) {                                   // two members per trip
       const int src = __ffs(members) - 1;
       members &= members - 1;
       const float *row = rows + src * STRIDE;
       if (has0) acc0 += row[c0];
       if (NV > 32 && has1) acc1 += row[c1];
+      if (members) {
+        const int src2 = __ffs(members) - 1;
+        members &= members - 1;
+        const float *row2 = rows + src2 * STRIDE;
+        if (has0) acc0 += row2[c0];
+        if (NV > 32 && has1) acc1 += row2[c1];
+      }
     }
     const float *lrow = rows + leader * STRIDE;
     if (has0) {
@@ -445,10 +452,10 @@ int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, 
     if (fused && d_attrs) PMR_CUDA(ctx, cudaMemsetAsync(d_attrs, 0, (size_t)n_pairs * A * sizeof(float), stream));
     if (total == 0 || T == 0) return PMR_OK;
     const int blocks_x = (W + 7) / 8, blocks_y = (H + 3) / 4;
-    const long long n_blocks = (long long)blocks_x * blocks_y * B;
+    const int blocks_per_image = blocks_x * blocks_y;
 #define PMR_BLOCKS(F, AS, WARPS)                                                                          \
-  backward_blocks_kernel<F, AS, WARPS><<<(unsigned)((n_blocks + WARPS - 1) / WARPS), WARPS * 32, 0, stream>>>(       \
-      grad, verts, attrs, tris, ids, bary, V, W, H, blocks_x, blocks_x * blocks_y, n_blocks, d_verts, d_attrs)
+  backward_blocks_kernel<F, AS, WARPS><<<dim3((blocks_per_image + WARPS - 1) / WARPS, B), WARPS * 32, 0, stream>>>(  \
+      grad, verts, attrs, tris, ids, bary, V, W, H, blocks_x, blocks_per_image, d_verts, d_attrs)
     if (!fused) PMR_BLOCKS(false, 1, 8);
     else if (A == 9) PMR_BLOCKS(true, 9, 8);
     else if (A == 4) PMR_BLOCKS(true, 4, 8);
