@@ -255,20 +255,36 @@ def main():
     ms_step = ms_total / args.steps
     value = world * P / (ms_step * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (device time from the library's per-stage CUDA events)
+    # ---- roofline of the dominant kernel (device time from the library's per-stage CUDA events).
+    # Algorithmic bytes (SURVEY 8d / BASELINE.md 4): forward writes ids 4 + bary 12 + z 4 + image 4A per
+    # pixel and reads each image's vertices, attributes and the index buffer once; backward reads
+    # grad 4A + ids 4 + bary 12 per pixel and writes each image's vertex / attribute gradients once.
+    # The forward is split over kernels: the scatter kernel's share is the mesh read, the resolve
+    # kernel's share is the per-pixel output (+ attributes); depth keys are overhead, not algorithmic.
     peak, peak_src = measured_peak_gbs()
     bytes_fwd = P * (20 + 4 * A) + B * (V * (16 + 4 * A) + 12 * T)
     bytes_bwd = P * (16 + 4 * A) + B * V * (16 + 4 * A)
+    kernel_bytes = {"scatter": B * (16 * V + 12 * T), "resolve": P * (20 + 4 * A) + B * V * 4 * A,
+                    "raster": bytes_fwd, "backward": bytes_bwd}
+    kernel_names = {"scatter": "scatter_small_kernel (small triangles -> packed depth keys)",
+                    "resolve": "resolve_kernel<9> (depth keys -> ids/bary/z + fused interpolation)",
+                    "raster": "raster_tile_kernel (tile path)",
+                    "backward": "backward_%s_kernel (fused interpolation backward)" % ("blocks" if args.mode == "atomic" else "ordered")}
     stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
-    dominant = "backward" if stage_ms["backward"] >= stage_ms["raster"] else "raster"
-    dom_bytes = bytes_bwd if dominant == "backward" else bytes_fwd
+    per_step = {k: v[0] / args.steps for k, v in stages.items()}
+    dominant = max(kernel_bytes, key=lambda k: per_step[k])
+    dom_bytes = kernel_bytes[dominant]
     achieved = dom_bytes / (stage_ms[dominant] * 1e-3) / 1e9 if stage_ms[dominant] > 0 else 0.0
+    fwd_ms = per_step["bin"] + per_step["scatter"] + per_step["raster"] + per_step["resolve"]
     roofline = {
-        "bound": "hbm", "kernel": {"raster": "raster_tile_kernel<9> (forward + fused interpolation)",
-                                   "backward": "backward_%s_kernel (fused interpolation backward)" % args.mode}[dominant],
+        "bound": "hbm", "kernel": kernel_names[dominant],
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": stage_ms[dominant],
-        "stages_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+        "stages_ms_per_step": per_step,
+        "forward": {"algorithmic_bytes": bytes_fwd, "ms": fwd_ms,
+                    "frac": bytes_fwd / (fwd_ms * 1e-3) / 1e9 / peak if fwd_ms > 0 else None},
+        "backward": {"algorithmic_bytes": bytes_bwd, "ms": per_step["backward"],
+                     "frac": bytes_bwd / (per_step["backward"] * 1e-3) / 1e9 / peak if per_step["backward"] > 0 else None},
         "step": {"algorithmic_bytes": bytes_fwd + bytes_bwd,
                  "achieved": (bytes_fwd + bytes_bwd) / (ms_step * 1e-3) / 1e9,
                  "frac": (bytes_fwd + bytes_bwd) / (ms_step * 1e-3) / 1e9 / peak},

@@ -82,11 +82,13 @@ PMR_API int pmr_set_small_mesh_threshold(pmr_context *ctx, int triangles);
  * running totals held by the context, copies the totals out and, if `reset` is non-zero,
  * clears them.
  */
-#define PMR_STAGE_BIN 0      /* bin_count + bin_offsets + length read-back + bin_fill */
-#define PMR_STAGE_RASTER 1   /* raster_tile_kernel (with fused interpolation when requested) */
+#define PMR_STAGE_BIN 0      /* key clear + bin_offsets + length read-back + bin_fill */
+#define PMR_STAGE_RASTER 1   /* raster_tile_kernel (big triangles; whole pass for tiny meshes) */
 #define PMR_STAGE_BACKWARD 2 /* backward kernels (atomic: one kernel; ordered: boxes + gather) */
 #define PMR_STAGE_INTERP 3   /* standalone interpolate_kernel */
-#define PMR_STAGE_COUNT 4
+#define PMR_STAGE_SCATTER 4  /* scatter_small_kernel (small triangles -> depth keys; bins the big ones) */
+#define PMR_STAGE_RESOLVE 5  /* resolve_kernel (depth keys -> ids / bary / z / interpolated image) */
+#define PMR_STAGE_COUNT 6
 PMR_API int pmr_enable_stage_timing(pmr_context *ctx, int enable);
 PMR_API int pmr_read_stage_timing(pmr_context *ctx, double *ms, long long *counts, int reset);
 

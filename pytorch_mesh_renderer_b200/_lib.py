@@ -111,7 +111,7 @@ def launch_count(device_index=None):
     return lib.pmr_launch_count(c) if c is not None else 0
 
 
-STAGES = ("bin", "raster", "backward", "interp")
+STAGES = ("bin", "raster", "backward", "interp", "scatter", "resolve")
 
 
 def enable_stage_timing(device_index, on=True):

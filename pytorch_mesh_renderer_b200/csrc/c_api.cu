@@ -128,6 +128,8 @@ void pmr_destroy(pmr_context *ctx) {
   ctx->bins.release();
   ctx->lists.release();
   ctx->scratch.release();
+  ctx->keys.release();
+  ctx->centers.release();
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
   for (const pmr::StageInterval &iv : ctx->intervals) { cudaEventDestroy(iv.begin); cudaEventDestroy(iv.end); }
   for (cudaEvent_t e : ctx->spare_events) cudaEventDestroy(e);

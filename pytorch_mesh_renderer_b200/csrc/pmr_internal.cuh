@@ -36,7 +36,8 @@ struct Context {
   int device = 0;
   int sm_count = 148;
   int small_mesh_threshold = 64;      // T at or below this: no binning, every tile walks all triangles
-  Buffer bins, lists, scratch;
+  Buffer bins, lists, scratch, keys, centers;
+  int centers_w = -1, centers_h = -1;  // image size the pixel-centre table was built for
   unsigned long long *mailbox = nullptr;   // pinned host word for the tile-list length
   unsigned long long last_bin_entries = 0;
   long long launches = 0;             // kernels launched through this context (bench gpu_launches)
@@ -45,8 +46,8 @@ struct Context {
   bool timing = false;
   std::vector<StageInterval> intervals;     // recorded, not yet read
   std::vector<cudaEvent_t> spare_events;
-  double stage_ms[PMR_STAGE_COUNT] = {0, 0, 0, 0};
-  long long stage_n[PMR_STAGE_COUNT] = {0, 0, 0, 0};
+  double stage_ms[PMR_STAGE_COUNT] = {};
+  long long stage_n[PMR_STAGE_COUNT] = {};
 };
 
 // RAII bracket around one stage: records an event pair on `stream` when timing is enabled.

@@ -1,30 +1,31 @@
-// raster_forward.cu -- screen-tile binning and the per-tile raster kernel (forward pass of
-// rasterize_triangles, K.cpp:302-419, batched over images) with the attribute interpolation
-// of rasterize_clip_space (rast.py:118-150) fused into its epilogue.
+// raster_forward.cu -- forward pass of rasterize_triangles (K.cpp:302-419, batched over images) with
+// the attribute interpolation of rasterize_clip_space (rast.py:118-150) fused into its last kernel.
 //
-// Pipeline per call (all on one stream):
-//   bin_count_kernel   one thread per (image, triangle): pixel box (kept, 8 bytes) -> per-tile counts
-//   bin_offsets_kernel warp-aggregated allocation of one contiguous list range per tile
-//   bin_fill_kernel    writes triangle ids into the tile lists (order inside a list is arbitrary)
-//   raster_tile_kernel one CTA per 16x16-pixel tile.  Triangle setup records (edge equations, z, w,
-//                      pixel box) are staged into shared memory 256 at a time and split by the size
-//                      of their box inside the tile:
-//                        small (<= 64 pixels): the boxes are cut into row segments of up to four
-//                          pixels, the segments of all small triangles are laid out back to back and
-//                          dealt to the 256 threads (balanced work whatever the triangle sizes);
-//                          a thread runs the inside test on its four pixels, the inside pixels of a
-//                          warp are compacted and dealt to its lanes again for barycentrics / depth,
-//                          and depth is resolved with a packed 64-bit atomicMin(depth bits, ~id) on a
-//                          shared-memory key per pixel;
-//                        big: one WARP per 8x4 pixel block culls the records with a ballot and each
-//                          lane tests its own pixel, keeping its winner in registers.
-//                      The per-pixel minimum of both paths is the winner; a winner that came through
-//                      the key buffer is re-evaluated once (same arithmetic, same bits) and ids /
-//                      barycentrics / z (+ interpolated attributes) are written.
-// Meshes with few triangles skip binning: every tile walks the whole triangle array.
+// Depth is resolved with ONE packed 64-bit key per pixel, (orderable depth bits << 32) | ~id, whose
+// minimum is the reference's winner (min z, then max id -- SURVEY.md F1).  Pipeline (one stream):
+//   scatter_small_kernel  one warp per 32 triangles of an image.  Triangles whose pixel box is at most
+//                         16x16 are rasterized right here: their boxes are cut into row segments of
+//                         <= 4 pixels, the segments of the warp's triangles are laid out back to back
+//                         in shared memory and dealt to the lanes (balanced whatever the sizes), the
+//                         inside pixels are compacted and dealt to the lanes again for barycentrics /
+//                         depth, and each one does atomicMin on the pixel's key in global memory (L2).
+//                         No per-tile duplication of triangle setup, no binning for these triangles.
+//                         Larger triangles are only counted into the 16x16 screen tiles they touch.
+//   bin_offsets_kernel    warp-aggregated allocation of one contiguous list range per tile
+//   bin_fill_kernel       writes the ids of the LARGE triangles into the tile lists
+//   raster_tile_kernel    one CTA per tile for the large triangles: setup records staged in shared
+//                         memory, a warp per 8x4 pixel block culls them with a ballot, one lane per
+//                         pixel keeps its winner in registers (parts of large triangles that are small
+//                         inside the tile take the segment path on a shared-memory key), result merged
+//                         into the global keys.  Skipped when no triangle is large.
+//   resolve_kernel        one warp per 8x4 pixel block: decodes the winner, re-evaluates its
+//                         barycentrics / depth once (same arithmetic, same bits), interpolates the
+//                         attributes and stores ids / z / barycentrics / image as 16-byte vectors
+//                         through a shared-memory transpose.
+// Meshes with few triangles (<= small_mesh_threshold) run raster_tile_kernel alone: every tile walks
+// the whole triangle array and writes the outputs itself.
 //
-// The depth rule is order independent (min z, then max id -- SURVEY.md F1), so neither list order
-// nor atomic order matters and the result is deterministic.
+// Neither list order nor atomic order can change a result, so the pass is deterministic.
 #include "pmr_internal.cuh"
 #include "raster_math.cuh"
 
@@ -84,23 +85,6 @@ __device__ __forceinline__ void for_each_tile(uint2 packed, int tiles_x, Visit v
       visit(ty * tiles_x + tx, src);
     }
   }
-}
-
-__global__ void __launch_bounds__(256)
-bin_count_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris,
-                 int V, int T, int W, int H, float half_w, float half_h, int tiles_x, int tiles_per_image,
-                 uint2 *__restrict__ tri_boxes, int *__restrict__ tile_counts) {
-  const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint2 packed = make_uint2(0u, 0u);
-  if (t < T) {
-    float4 p0, p1, p2;
-    load_triangle(verts + (size_t)b * V * 4, tris, t, p0, p1, p2);
-    packed = pack_box(triangle_box(p0, p1, p2, half_w, half_h, W, H));
-    tri_boxes[(size_t)b * T + t] = packed;
-  }
-  int *counts = tile_counts + (size_t)b * tiles_per_image;
-  for_each_tile(packed, tiles_x, [&](int tile, int) { atomicAdd(counts + tile, 1); });
 }
 
 // One contiguous range per tile; ranges are handed out warp by warp from a global cursor, so
@@ -219,6 +203,75 @@ __device__ __forceinline__ void store_block_rows(const float *stage, float *dst_
   }
 }
 
+// Barycentrics / depth of a known winner (triangle t covers the pixel and passed the depth range).
+__device__ __forceinline__ void evaluate_winner(const float4 &p0, const float4 &p1, const float4 &p2,
+                                                float px, float py, int t, Fragment &out) {
+  float m[9], e[3], esum, bc[3], z;
+  adjugate_signed(p0.x, p1.x, p2.x, p0.y, p1.y, p2.y, p0.w, p1.w, p2.w, m);
+  edge_values(m, px, py, e);
+  edges_inside(e, esum);
+  const float zc[3] = {p0.z, p1.z, p2.z}, wc[3] = {p0.w, p1.w, p2.w};
+  fragment_depth(e, esum, zc, wc, bc, z);
+  out.z = z; out.id = t; out.b0 = bc[0]; out.b1 = bc[1]; out.b2 = bc[2];
+}
+
+// Output of one warp's 8x4 pixel block (lane = pixel): ids / z / barycentrics and, when requested, the
+// interpolated attributes of rast.py:118-150, transposed through `stage` (32*16 floats of shared
+// memory owned by the warp) so that global stores are whole 16-byte vectors.
+template <int A_STATIC>
+__device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, int blk_y0, int W, int H, int V,
+                                               const Fragment &best, const int32_t *__restrict__ tris,
+                                               const float *__restrict__ attrs, const float *__restrict__ background,
+                                               int A, int32_t *__restrict__ out_ids, float *__restrict__ out_bary,
+                                               float *__restrict__ out_z, float *__restrict__ out_image) {
+  const int lane = threadIdx.x & 31;
+  const bool covered = best.id >= 0;
+  const int id = covered ? best.id : 0;
+  const int cols = min(8, W - blk_x0), rows = min(4, H - blk_y0);     // <= 0: block outside the image
+  if (cols <= 0 || rows <= 0) return;
+  const bool vec_ok = (W & 3) == 0 &&
+      (((uintptr_t)out_ids | (uintptr_t)out_z | (uintptr_t)out_bary | (uintptr_t)out_image) & 15) == 0;
+  const size_t p0 = ((size_t)b * H + blk_y0) * W + blk_x0;            // first pixel of the block
+  stage[lane] = __int_as_float(id);
+  stage[32 + lane] = best.z;
+  stage[64 + 3 * lane + 0] = best.b0;
+  stage[64 + 3 * lane + 1] = best.b1;
+  stage[64 + 3 * lane + 2] = best.b2;
+  __syncwarp();
+  store_block_rows<1>(stage, reinterpret_cast<float *>(out_ids) + p0, (size_t)W, cols, rows, vec_ok);
+  store_block_rows<1>(stage + 32, out_z + p0, (size_t)W, cols, rows, vec_ok);
+  store_block_rows<3>(stage + 64, out_bary + 3 * p0, (size_t)W * 3, cols, rows, vec_ok);
+  __syncwarp();
+  if (out_image == nullptr) return;
+
+  // rast.py:118-150: corner attributes weighted by barycentrics, alpha, background blend.
+  const bool staged = A_STATIC > 0 && A_STATIC <= 16;   // compiled-in attribute counts use the staging area
+  float *direct = out_image + (p0 + (size_t)(lane >> 3) * W + (lane & 7)) * A;
+  float *dst = staged ? stage + lane * A : direct;
+  const bool in_image = (lane & 7) < cols && (lane >> 3) < rows;
+  if (staged || in_image) {
+    if (!covered) {
+      for (int a = 0; a < A; ++a) dst[a] = __ldg(background + a);
+    } else {
+      const float *at = attrs + (size_t)b * V * A;
+      const float *c0 = at + (size_t)__ldg(tris + 3 * (size_t)id + 0) * A;
+      const float *c1 = at + (size_t)__ldg(tris + 3 * (size_t)id + 1) * A;
+      const float *c2 = at + (size_t)__ldg(tris + 3 * (size_t)id + 2) * A;
+      const float alpha = coverage_alpha(best.b0, best.b1, best.b2);
+      const float one_minus = 1.0f - alpha;
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        const float img = __ldg(c0 + a) * best.b0 + __ldg(c1 + a) * best.b1 + __ldg(c2 + a) * best.b2;
+        dst[a] = alpha * img + one_minus * __ldg(background + a);
+      }
+    }
+  }
+  if (staged) {
+    __syncwarp();
+    store_block_rows<(A_STATIC > 0 ? A_STATIC : 1)>(stage, out_image + p0 * A, (size_t)W * A, cols, rows, vec_ok);
+  }
+}
+
 template <int A_STATIC>
 __global__ void __launch_bounds__(kChunk, 5)
 raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris,
@@ -227,7 +280,7 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
                    const int32_t *__restrict__ tile_lists, const uint2 *__restrict__ tri_boxes,
                    int32_t *__restrict__ out_ids, float *__restrict__ out_bary, float *__restrict__ out_z,
                    const float *__restrict__ attrs, const float *__restrict__ background, int A_dyn,
-                   float *__restrict__ out_image) {
+                   float *__restrict__ out_image, unsigned long long *__restrict__ keys_out) {
   __shared__ __align__(16) TileSmem sm;
   const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
   const int b = blockIdx.z;
@@ -394,72 +447,204 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
   }
   __syncthreads();           // all keys final; record planes dead from here on
 
-  // ---- resolve: minimum of the two paths; re-evaluate the winner if it came from the key buffer
+  // ---- resolve: minimum of the two paths
   const unsigned long long key_small = sm.key[ly * kTileW + lx];
   const unsigned long long key_big = best.id >= 0 ? depth_key(best.z, best.id) : kEmptyKey;
-  if (key_small < key_big) {
+  if (keys_out != nullptr) {
+    // large-triangle pass of the binned pipeline: merge into the global keys (this CTA is the only
+    // writer of its pixels now; the scatter kernel has finished), resolve_kernel does the rest.
+    if (ix < W && iy < H) {
+      const size_t p = ((size_t)b * H + iy) * W + ix;
+      const unsigned long long mine = min(key_small, key_big);
+      if (mine < keys_out[p]) keys_out[p] = mine;
+    }
+    return;
+  }
+  if (key_small < key_big) {     // the winner came through the key buffer: re-evaluate it once
     const int t = depth_key_id(key_small);
     float4 p0, p1, p2;
     load_triangle(verts_b, tris, t, p0, p1, p2);
-    float m[9], e[3], esum, bc[3], z;
-    adjugate_signed(p0.x, p1.x, p2.x, p0.y, p1.y, p2.y, p0.w, p1.w, p2.w, m);
-    edge_values(m, px, py, e);
-    edges_inside(e, esum);
-    const float zc[3] = {p0.z, p1.z, p2.z}, wc[3] = {p0.w, p1.w, p2.w};
-    fragment_depth(e, esum, zc, wc, bc, z);
-    best.z = z; best.id = t; best.b0 = bc[0]; best.b1 = bc[1]; best.b2 = bc[2];
+    evaluate_winner(p0, p1, p2, px, py, t, best);
   }
-  const bool covered = best.id >= 0;
-  const int id = covered ? best.id : 0;
-
-  // ---- epilogue: transpose the warp's block through shared memory, store whole 16-byte vectors
   float *stage = reinterpret_cast<float *>(sm.r0) + warp * (32 * 16);
-  const int cols = min(8, W - blk_x0), rows = min(4, H - blk_y0);     // <= 0: block outside the image
-  if (cols <= 0 || rows <= 0) return;
-  const bool vec_ok = (W & 3) == 0 &&
-      (((uintptr_t)out_ids | (uintptr_t)out_z | (uintptr_t)out_bary | (uintptr_t)out_image) & 15) == 0;
-  const size_t p0 = ((size_t)b * H + blk_y0) * W + blk_x0;            // first pixel of the block
-  // ids (as raw bits), z, barycentrics
-  stage[lane] = __int_as_float(id);
-  stage[32 + lane] = best.z;
-  stage[64 + 3 * lane + 0] = best.b0;
-  stage[64 + 3 * lane + 1] = best.b1;
-  stage[64 + 3 * lane + 2] = best.b2;
-  __syncwarp();
-  store_block_rows<1>(stage, reinterpret_cast<float *>(out_ids) + p0, (size_t)W, cols, rows, vec_ok);
-  store_block_rows<1>(stage + 32, out_z + p0, (size_t)W, cols, rows, vec_ok);
-  store_block_rows<3>(stage + 64, out_bary + 3 * p0, (size_t)W * 3, cols, rows, vec_ok);
-  __syncwarp();
+  block_epilogue<A_STATIC>(stage, b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
+                           out_ids, out_bary, out_z, out_image);
+}
 
-  if (out_image != nullptr) {
-    // rast.py:118-150: corner attributes weighted by barycentrics, alpha, background blend.
-    float *o = stage + lane * A;                      // compiled-in attribute counts go through the staging area
-    const bool staged = A_STATIC > 0 && A_STATIC <= 16;
-    float *direct = out_image + (p0 + (size_t)(lane >> 3) * W + (lane & 7)) * A;
-    float *dst = staged ? o : direct;
-    const bool in_image = (lane & 7) < cols && (lane >> 3) < rows;
-    if (staged || in_image) {
-      if (!covered) {
-        for (int a = 0; a < A; ++a) dst[a] = __ldg(background + a);
+// ---------------------------------------------------------------------------------------------
+// Small triangles: global scatter
+// ---------------------------------------------------------------------------------------------
+
+// Pixel-centre NDC coordinates of every column and row (K.cpp:376-377), built once per image size.
+__global__ void pixel_centers_kernel(float *__restrict__ centers, int W, int H, float half_w, float half_h) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W) centers[i] = pixel_center(i, half_w);
+  else if (i < W + H) centers[i] = pixel_center(i - W, half_h);
+}
+
+constexpr int kScatterWarps = 8;
+constexpr int kScatterSegCap = 512;          // row segments a warp holds per round (one triangle has <= 64)
+constexpr int kSmallBox = 16;                // largest box side the scatter path takes
+
+struct ScatterWarpSmem {
+  float4 r0[32], r1[32], r2[32], r3[32];     // setup records of the warp's 32 triangles (planes as in TileSmem)
+  int2 origin[32];                           // left, bottom of each triangle's pixel box
+  unsigned short segs[kScatterSegCap];       // slot | dy << 5 | dx << 9 | width << 13
+  unsigned short hits[128];                  // slot | dy << 5 | x offset << 9
+};
+
+__global__ void __launch_bounds__(kScatterWarps * 32)
+scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int T, int W, int H,
+                     float half_w, float half_h, int tiles_x, int tiles_per_image,
+                     const float *__restrict__ centers, uint2 *__restrict__ tri_boxes,
+                     int *__restrict__ tile_counts, unsigned long long *__restrict__ keys) {
+  __shared__ __align__(16) ScatterWarpSmem sm_all[kScatterWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ScatterWarpSmem &sm = sm_all[warp];
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const float *cx = centers, *cy = centers + W;
+  unsigned long long *keys_b = keys + (size_t)b * H * W;
+
+  // ---- setup: one triangle per lane
+  int n_seg = 0, bw = 0, bh = 0;
+  uint2 big_box = make_uint2(0u, 0u);
+  if (t < T) {
+    float4 p0, p1, p2;
+    load_triangle(verts + (size_t)b * V * 4, tris, t, p0, p1, p2);
+    const PixelBox box = triangle_box(p0, p1, p2, half_w, half_h, W, H);
+    bw = box.right - box.left; bh = box.top - box.bottom;
+    if (bw > 0 && bh > 0) {
+      if (bw <= kSmallBox && bh <= kSmallBox) {
+        float m[9];
+        adjugate_signed(p0.x, p1.x, p2.x, p0.y, p1.y, p2.y, p0.w, p1.w, p2.w, m);
+        sm.r0[lane] = make_float4(m[0], m[1], m[2], __int_as_float(t));
+        sm.r1[lane] = make_float4(m[3], m[4], m[5], p0.z);
+        sm.r2[lane] = make_float4(m[6], m[7], m[8], p1.z);
+        sm.r3[lane] = make_float4(p2.z, p0.w, p1.w, p2.w);
+        sm.origin[lane] = make_int2(box.left, box.bottom);
+        n_seg = bh * ((bw + 3) >> 2);
       } else {
-        const float *at = attrs + (size_t)b * V * A;
-        const float *c0 = at + (size_t)__ldg(tris + 3 * (size_t)id + 0) * A;
-        const float *c1 = at + (size_t)__ldg(tris + 3 * (size_t)id + 1) * A;
-        const float *c2 = at + (size_t)__ldg(tris + 3 * (size_t)id + 2) * A;
-        const float alpha = coverage_alpha(best.b0, best.b1, best.b2);
-        const float one_minus = 1.0f - alpha;
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-          const float img = __ldg(c0 + a) * best.b0 + __ldg(c1 + a) * best.b1 + __ldg(c2 + a) * best.b2;
-          dst[a] = alpha * img + one_minus * __ldg(background + a);
-        }
+        big_box = pack_box(box);
       }
     }
-    if (staged) {
+    tri_boxes[(size_t)b * T + t] = big_box;            // empty for small triangles: bin_fill skips them
+  }
+  // large triangles are only counted into the tiles they touch (raster_tile_kernel draws them)
+  int *counts = tile_counts + (size_t)b * tiles_per_image;
+  for_each_tile(big_box, tiles_x, [&](int tile, int) { atomicAdd(counts + tile, 1); });
+
+  // ---- rounds: the longest prefix (in lane order) of the remaining small triangles whose segments fit
+  unsigned remaining = __ballot_sync(0xffffffffu, n_seg > 0);
+  while (remaining) {
+    const int mine = (remaining >> lane) & 1u ? n_seg : 0;
+    const int seg_end = warp_inclusive_scan(mine);
+    const bool fits = mine > 0 && seg_end <= kScatterSegCap;
+    if (fits) {
+      int k = seg_end - mine;
+      const int per_row = (bw + 3) >> 2;               // 1..4 segments per row
+      for (int dy = 0; dy < bh; ++dy) {
+        const unsigned head = lane | (dy << 5);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < per_row) sm.segs[k + q] = (unsigned short)(head | ((4 * q) << 9) | (min(4, bw - 4 * q) << 13));
+        k += per_row;
+      }
+    }
+    int total_segs = fits ? seg_end : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) total_segs = max(total_segs, __shfl_xor_sync(0xffffffffu, total_segs, d));
+    remaining &= ~__ballot_sync(0xffffffffu, fits);
+    __syncwarp();
+
+    for (int s0 = 0; s0 < total_segs; s0 += 32) {
+      // pass 1: inside test on the (up to) four pixels of this lane's segment
+      unsigned seg = 0u, inside = 0u;
+      if (s0 + lane < total_segs) {
+        seg = sm.segs[s0 + lane];
+        const int j = seg & 31u, dy = (seg >> 5) & 15u, dx = (seg >> 9) & 15u, width = seg >> 13;
+        const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j];
+        const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
+        const int2 org = sm.origin[j];
+        const float cyv = __ldg(cy + org.y + dy);
+        const float *cxp = cx + org.x + dx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < width) {
+            float e[3], esum;
+            edge_values(m, __ldg(cxp + k), cyv, e);
+            if (edges_inside(e, esum)) inside |= 1u << k;
+          }
+        }
+      }
+      // compact the inside pixels of the warp and deal them to the lanes again
+      const int mine_hits = __popc(inside);
+      const int upto = warp_inclusive_scan(mine_hits);
+      const int n_hits = __shfl_sync(0xffffffffu, upto, 31);
+      int at = upto - mine_hits;
+      while (inside) {
+        const int k = __ffs(inside) - 1;
+        inside &= inside - 1;
+        sm.hits[at++] = (unsigned short)((seg & 0x1ffu) | ((((seg >> 9) & 15u) + k) << 9));
+      }
       __syncwarp();
-      store_block_rows<(A_STATIC > 0 ? A_STATIC : 1)>(stage, out_image + p0 * A, (size_t)W * A, cols, rows, vec_ok);
+      // pass 2: barycentrics / depth for exactly those pixels, depth resolve by packed atomicMin (L2)
+      for (int h = lane; h < n_hits; h += 32) {
+        const unsigned hit = sm.hits[h];
+        const int j = hit & 31u, dy = (hit >> 5) & 15u, xo = hit >> 9;
+        const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j], q3 = sm.r3[j];
+        const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
+        const float zc[3] = {q1.w, q2.w, q3.x};
+        const float wc[3] = {q3.y, q3.z, q3.w};
+        const int2 org = sm.origin[j];
+        const int x = org.x + xo, y = org.y + dy;
+        float e[3], esum, bc[3], z;
+        edge_values(m, __ldg(cx + x), __ldg(cy + y), e);
+        edges_inside(e, esum);
+        if (fragment_depth(e, esum, zc, wc, bc, z))
+          atomicMin(keys_b + (size_t)y * W + x, depth_key(z, __float_as_int(q0.w)));
+      }
+      __syncwarp();
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resolve: depth keys -> outputs
+// ---------------------------------------------------------------------------------------------
+
+constexpr int kResolveWarps = 8;
+
+template <int A_STATIC>
+__global__ void __launch_bounds__(kResolveWarps * 32)
+resolve_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int W, int H,
+               int blocks_x, int blocks_per_image, const float *__restrict__ centers,
+               const unsigned long long *__restrict__ keys,
+               int32_t *__restrict__ out_ids, float *__restrict__ out_bary, float *__restrict__ out_z,
+               const float *__restrict__ attrs, const float *__restrict__ background, int A_dyn,
+               float *__restrict__ out_image) {
+  __shared__ __align__(16) float stage_all[kResolveWarps][32 * 16];
+  const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rem = blockIdx.x * kResolveWarps + warp;
+  if (rem >= blocks_per_image) return;
+  const int b = blockIdx.y;
+  const int by = rem / blocks_x;
+  const int blk_x0 = (rem - by * blocks_x) * 8, blk_y0 = by * 4;
+  const int ix = blk_x0 + (lane & 7), iy = blk_y0 + (lane >> 3);
+  Fragment best;
+  fragment_clear(best);
+  if (ix < W && iy < H) {
+    const unsigned long long key = keys[((size_t)b * H + iy) * W + ix];
+    if (key != kEmptyKey) {
+      const int t = depth_key_id(key);
+      float4 p0, p1, p2;
+      load_triangle(verts + (size_t)b * V * 4, tris, t, p0, p1, p2);
+      evaluate_winner(p0, p1, p2, __ldg(centers + ix), __ldg(centers + W + iy), t, best);
+    }
+  }
+  block_epilogue<A_STATIC>(stage_all[warp], b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
+                           out_ids, out_bary, out_z, out_image);
 }
 
 // Standalone interpolation (rast.py:118-150) from existing id / barycentric buffers.
@@ -493,7 +678,7 @@ interpolate_kernel(const float *__restrict__ attrs, const int32_t *__restrict__ 
 static int launch_raster(Context *ctx, const float *verts, const int32_t *tris, int B, int V, int T,
                          int W, int H, const int *counts, const int *offsets, const int32_t *lists,
                          const uint2 *boxes, int32_t *ids, float *bary, float *z, const float *attrs, const float *bg, int A,
-                         float *image, cudaStream_t stream) {
+                         float *image, unsigned long long *keys_out, cudaStream_t stream) {
   const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
   const int tiles = tiles_x * tiles_y;
   const float half_w = (float)(0.5 * W), half_h = (float)(0.5 * H);   // K.cpp:309-310
@@ -502,8 +687,8 @@ static int launch_raster(Context *ctx, const float *verts, const int32_t *tris, 
 #define PMR_LAUNCH(AS)                                                                              \
   raster_tile_kernel<AS><<<grid, kChunk, 0, stream>>>(verts, tris, V, T, W, H, half_w, half_h,      \
                                                      tiles, counts, offsets, lists, boxes, ids,     \
-                                                     bary, z, attrs, bg, A, image)
-  if (image == nullptr) PMR_LAUNCH(0);
+                                                     bary, z, attrs, bg, A, image, keys_out)
+  if (image == nullptr || keys_out != nullptr) PMR_LAUNCH(0);
   else if (A == 4) PMR_LAUNCH(4);
   else if (A == 9) PMR_LAUNCH(9);
   else if (A == 12) PMR_LAUNCH(12);
@@ -523,55 +708,95 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
   const float half_w = (float)(0.5 * W), half_h = (float)(0.5 * H);
 
   if (T <= ctx->small_mesh_threshold) {
+    // tiny mesh: one kernel, every tile walks all triangles and writes the outputs itself
     return launch_raster(ctx, verts, tris, B, V, T, W, H, nullptr, nullptr, nullptr, nullptr, ids, bary, z, attrs,
-                         bg, A, image, stream);
+                         bg, A, image, nullptr, stream);
   }
 
-  const size_t n_tiles = (size_t)B * tiles;
-  int32_t *lists = nullptr;
-  int *counts = nullptr, *offsets = nullptr;
-  uint2 *ranges = nullptr;      // packed pixel box per (image, triangle)
-  {
-  StageScope timed(ctx, PMR_STAGE_BIN, stream);
+  const size_t n_tiles = (size_t)B * tiles, n_pixels = (size_t)B * H * W;
   if (n_tiles > (size_t)INT_MAX) return set_error(ctx, PMR_ERR_SIZE, "too many screen tiles");
-  // workspace: [total u64 | counts | cursors | offsets | ranges]
-  int rc = ctx->bins.reserve(ctx, 16 + n_tiles * 3 * sizeof(int) + (size_t)B * T * sizeof(uint2) + 64);
+  int rc;
+  // pixel-centre table of this image size (rebuilt only when the size changes)
+  if (ctx->centers_w != W || ctx->centers_h != H) {
+    rc = ctx->centers.reserve(ctx, (size_t)(W + H) * sizeof(float));
+    if (rc) return rc;
+    pixel_centers_kernel<<<(W + H + 255) / 256, 256, 0, stream>>>((float *)ctx->centers.ptr, W, H, half_w, half_h);
+    ctx->launches += 1;
+    ctx->centers_w = W; ctx->centers_h = H;
+  }
+  const float *centers = (const float *)ctx->centers.ptr;
+  // workspace: [total u64 | counts | cursors | offsets | boxes], keys
+  rc = ctx->bins.reserve(ctx, 16 + n_tiles * 3 * sizeof(int) + (size_t)B * T * sizeof(uint2) + 64);
+  if (rc) return rc;
+  rc = ctx->keys.reserve(ctx, n_pixels * sizeof(unsigned long long));
   if (rc) return rc;
   char *base = (char *)ctx->bins.ptr;
   unsigned long long *total = (unsigned long long *)base;
-  counts = (int *)(base + 16);
+  int *counts = (int *)(base + 16);
   int *cursors = counts + n_tiles;
-  offsets = cursors + n_tiles;
-  ranges = (uint2 *)(((uintptr_t)(offsets + n_tiles) + 15) & ~(uintptr_t)15);
+  int *offsets = cursors + n_tiles;
+  uint2 *boxes = (uint2 *)(((uintptr_t)(offsets + n_tiles) + 15) & ~(uintptr_t)15);
+  unsigned long long *keys = (unsigned long long *)ctx->keys.ptr;
 
-  PMR_CUDA(ctx, cudaMemsetAsync(base, 0, 16 + n_tiles * 2 * sizeof(int), stream));
-  dim3 tgrid((T + 255) / 256, B);
-  bin_count_kernel<<<tgrid, 256, 0, stream>>>(verts, tris, V, T, W, H, half_w, half_h, tiles_x, tiles,
-                                             ranges, counts);
-  bin_offsets_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(counts, (int)n_tiles, offsets,
-                                                                           total);
-  ctx->launches += 2;
-  rc = check_launch(ctx, "bin_count/bin_offsets");
-  if (rc) return rc;
-
-  // The list length is data dependent: read it back (8 bytes, pinned) to size the buffer.
-  PMR_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, total, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                stream));
-  PMR_CUDA(ctx, cudaStreamSynchronize(stream));
-  const unsigned long long n_entries = *ctx->mailbox;
-  ctx->last_bin_entries = n_entries;
-  if (n_entries >= (1ull << 31)) return set_error(ctx, PMR_ERR_SIZE, "tile lists exceed 2^31 entries");
-  rc = ctx->lists.reserve(ctx, (size_t)(n_entries + 1) * sizeof(int32_t));
-  if (rc) return rc;
-  lists = (int32_t *)ctx->lists.ptr;
-
-  bin_fill_kernel<<<tgrid, 256, 0, stream>>>(ranges, T, tiles_x, tiles, offsets, cursors, lists);
-  ctx->launches += 1;
-  rc = check_launch(ctx, "bin_fill_kernel");
-  if (rc) return rc;
+  {
+    StageScope timed(ctx, PMR_STAGE_BIN, stream);
+    PMR_CUDA(ctx, cudaMemsetAsync(base, 0, 16 + n_tiles * 2 * sizeof(int), stream));
+    PMR_CUDA(ctx, cudaMemsetAsync(keys, 0xff, n_pixels * sizeof(unsigned long long), stream));   // kEmptyKey
   }
-  return launch_raster(ctx, verts, tris, B, V, T, W, H, counts, offsets, lists, ranges, ids, bary, z, attrs, bg, A,
-                       image, stream);
+  {
+    StageScope timed(ctx, PMR_STAGE_SCATTER, stream);
+    scatter_small_kernel<<<dim3((T + kScatterWarps * 32 - 1) / (kScatterWarps * 32), B), kScatterWarps * 32, 0, stream>>>(
+        verts, tris, V, T, W, H, half_w, half_h, tiles_x, tiles, centers, boxes, counts, keys);
+    ctx->launches += 1;
+    rc = check_launch(ctx, "scatter_small_kernel");
+    if (rc) return rc;
+  }
+  unsigned long long n_entries = 0;
+  {
+    StageScope timed(ctx, PMR_STAGE_BIN, stream);
+    bin_offsets_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(counts, (int)n_tiles, offsets, total);
+    ctx->launches += 1;
+    rc = check_launch(ctx, "bin_offsets_kernel");
+    if (rc) return rc;
+    // The list length of the large triangles is data dependent: read it back (8 bytes, pinned).
+    PMR_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    PMR_CUDA(ctx, cudaStreamSynchronize(stream));
+    n_entries = *ctx->mailbox;
+    ctx->last_bin_entries = n_entries;
+    if (n_entries >= (1ull << 31)) return set_error(ctx, PMR_ERR_SIZE, "tile lists exceed 2^31 entries");
+    if (n_entries > 0) {
+      rc = ctx->lists.reserve(ctx, (size_t)(n_entries + 1) * sizeof(int32_t));
+      if (rc) return rc;
+      bin_fill_kernel<<<dim3((T + 255) / 256, B), 256, 0, stream>>>(boxes, T, tiles_x, tiles, offsets, cursors,
+                                                                    (int32_t *)ctx->lists.ptr);
+      ctx->launches += 1;
+      rc = check_launch(ctx, "bin_fill_kernel");
+      if (rc) return rc;
+    }
+  }
+  if (n_entries > 0) {
+    rc = launch_raster(ctx, verts, tris, B, V, T, W, H, counts, offsets, (const int32_t *)ctx->lists.ptr, boxes,
+                       ids, bary, z, attrs, bg, A, image, keys, stream);
+    if (rc) return rc;
+  }
+  {
+    StageScope timed(ctx, PMR_STAGE_RESOLVE, stream);
+    const int blocks_x = (W + 7) / 8, blocks_y = (H + 3) / 4, bpi = blocks_x * blocks_y;
+    dim3 grid((bpi + kResolveWarps - 1) / kResolveWarps, B);
+#define PMR_RESOLVE(AS)                                                                                          \
+  resolve_kernel<AS><<<grid, kResolveWarps * 32, 0, stream>>>(verts, tris, V, W, H, blocks_x, bpi, centers, keys, ids, \
+                                                              bary, z, attrs, bg, A, image)
+    if (image == nullptr) PMR_RESOLVE(0);
+    else if (A == 4) PMR_RESOLVE(4);
+    else if (A == 9) PMR_RESOLVE(9);
+    else if (A == 12) PMR_RESOLVE(12);
+    else if (A == 13) PMR_RESOLVE(13);
+    else PMR_RESOLVE(0);
+#undef PMR_RESOLVE
+    ctx->launches += 1;
+    rc = check_launch(ctx, "resolve_kernel");
+  }
+  return rc;
 }
 
 int interpolate_impl(Context *ctx, const float *attrs, const int32_t *tris, const int32_t *ids,
