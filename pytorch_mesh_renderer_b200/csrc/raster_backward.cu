@@ -32,13 +32,11 @@ struct PixelGrad {
 // through the interpolation), and evaluates the nine vertex terms.
 //   fused:  d_img_a = g_a * alpha;  d_b_k = sum_a d_img_a * corner_k[a]  (torch order).
 template <bool FUSED>
-__device__ __forceinline__ void pixel_grad(const float *__restrict__ verts_b, const float *__restrict__ attrs_b,
-                                           const int32_t *__restrict__ tris, int id, const float *bary_p,
-                                           const float *g_p, int A, PixelGrad &out) {
+__device__ __forceinline__ void pixel_grad_loaded(const int vid[3], const float4 &p0, const float4 &p1, const float4 &p2,
+                                                  const float *__restrict__ attrs_b, const float *bary_p,
+                                                  const float *g_p, int A, PixelGrad &out) {
 #pragma unroll
-  for (int j = 0; j < 3; ++j) out.vid[j] = __ldg(tris + 3 * (size_t)id + j);
-  const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
-  const float4 p0 = __ldg(v4 + out.vid[0]), p1 = __ldg(v4 + out.vid[1]), p2 = __ldg(v4 + out.vid[2]);
+  for (int j = 0; j < 3; ++j) out.vid[j] = vid[j];
   out.b[0] = bary_p[0]; out.b[1] = bary_p[1]; out.b[2] = bary_p[2];
   float g[3];
   if (FUSED) {
@@ -61,6 +59,18 @@ __device__ __forceinline__ void pixel_grad(const float *__restrict__ verts_b, co
   float m[9];
   const float det = adjugate_signed(p0.x, p1.x, p2.x, p0.y, p1.y, p2.y, p0.w, p1.w, p2.w, m);
   vertex_terms(m, fabsf(det), out.b, g, out.terms);
+}
+
+template <bool FUSED>
+__device__ __forceinline__ void pixel_grad(const float *__restrict__ verts_b, const float *__restrict__ attrs_b,
+                                           const int32_t *__restrict__ tris, int id, const float *bary_p,
+                                           const float *g_p, int A, PixelGrad &out) {
+  int vid[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) vid[j] = __ldg(tris + 3 * (size_t)id + j);
+  const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
+  const float4 p0 = __ldg(v4 + vid[0]), p1 = __ldg(v4 + vid[1]), p2 = __ldg(v4 + vid[2]);
+  pixel_grad_loaded<FUSED>(vid, p0, p1, p2, attrs_b, bary_p, g_p, A, out);
 }
 
 __device__ __forceinline__ bool pixel_is_covered(int id, const float *bary_p) {
@@ -180,7 +190,7 @@ backward_atomic_kernel(const float *__restrict__ grad, const float *__restrict__
 // (profiles/microbench/atomics_bench.cu: 3.8x the lane rate of scattered atomics).
 
 template <bool FUSED, int A_STATIC, int kBlockWarps>
-__global__ void __launch_bounds__(kBlockWarps * 32)
+__global__ void __launch_bounds__(kBlockWarps * 32, (kBlockWarps == 8 ? 5 : 8))
 backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__ verts,
                        const float *__restrict__ attrs, const int32_t *__restrict__ tris,
                        const int32_t *__restrict__ ids, const float *__restrict__ bary,
@@ -189,8 +199,10 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
   constexpr int A = A_STATIC;
   constexpr int NV = 9 + (FUSED ? 3 * A : 0);
   constexpr int STRIDE = (NV + 3) | 1;           // NV sums + 3 vertex ids, odd => conflict-free rows
-  __shared__ float rows_all[kBlockWarps][32 * STRIDE];
-  __shared__ float stage_all[kBlockWarps][FUSED ? 32 * A : 1];
+  // per warp: 32 rows of NV sums + 3 vertex ids; the gradient staging area aliases the rows (it is
+  // consumed into registers before the first row is written)
+  __shared__ __align__(16) float rows_all[kBlockWarps][32 * STRIDE + 4];
+  static_assert(32 * STRIDE >= 32 * A, "gradient staging must fit the row area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rem = blockIdx.x * kBlockWarps + warp;        // 8x4 block within the image
@@ -214,36 +226,68 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
 
   float *rows = rows_all[warp];
   float g_local[FUSED ? A : 3];
+  // Start the dependent chain ids -> triangle -> vertices first, so that its latency overlaps the
+  // streaming loads of the gradient rows.
+  const float *verts_b = verts + (size_t)b * V * 4;
+  const float *attrs_b = FUSED ? attrs + (size_t)b * V * A : nullptr;
+  int vid[3] = {0, 0, 0};
+  if (id >= 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) vid[j] = __ldg(tris + 3 * (size_t)id + j);
+  }
+  float4 pv0 = make_float4(0.f, 0.f, 0.f, 0.f), pv1 = pv0, pv2 = pv0;
   if (FUSED) {
     // Stage the block's gradient rows through shared memory: a block row is 8*A contiguous
     // floats, read as float4 when the image rows keep them 16-byte aligned.
-    float *stage = stage_all[warp];
+    float *stage = rows;
     if ((W & 7) == 0) {
       constexpr int V4_PER_ROW = 2 * A;          // 8*A floats
+      constexpr int N_V4 = 4 * V4_PER_ROW;
+      constexpr int PER_LANE = (N_V4 + 31) / 32;
+      float4 held[PER_LANE];
+      const float *block_grad = grad + (((long long)b * H + y0) * W + x0) * A;   // first pixel of the block
 #pragma unroll
-      for (int k = lane; k < 4 * V4_PER_ROW; k += 32) {
-        const int r = k / V4_PER_ROW, c = k % V4_PER_ROW;
-        if (y0 + r < H) {
-          const float4 v = __ldg(reinterpret_cast<const float4 *>(grad + (((long long)b * H + y0 + r) * W + x0) * A) + c);
-          reinterpret_cast<float4 *>(stage + r * 8 * A)[c] = v;
-        }
+      for (int i = 0; i < PER_LANE; ++i) {
+        const int k = lane + 32 * i;
+        const int r = k / V4_PER_ROW, c = k - r * V4_PER_ROW;
+        if (k < N_V4 && y0 + r < H)
+          held[i] = __ldg(reinterpret_cast<const float4 *>(block_grad + (r * W * A + 4 * c)));
+      }
+      if (id >= 0) {
+        const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
+        pv0 = __ldg(v4 + vid[0]); pv1 = __ldg(v4 + vid[1]); pv2 = __ldg(v4 + vid[2]);
+      }
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) {
+        const int k = lane + 32 * i;
+        const int r = k / V4_PER_ROW;
+        if (k < N_V4 && y0 + r < H) reinterpret_cast<float4 *>(stage)[k] = held[i];     // rows back to back
       }
       __syncwarp();
 #pragma unroll
       for (int a = 0; a < A; ++a) g_local[a] = stage[lane * A + a];
-    } else if (in_image) {
+      __syncwarp();                               // staging consumed; the area becomes the rows
+    } else {
+      if (in_image) {
 #pragma unroll
-      for (int a = 0; a < A; ++a) g_local[a] = __ldg(grad + p * A + a);
+        for (int a = 0; a < A; ++a) g_local[a] = __ldg(grad + p * A + a);
+      }
+      if (id >= 0) {
+        const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
+        pv0 = __ldg(v4 + vid[0]); pv1 = __ldg(v4 + vid[1]); pv2 = __ldg(v4 + vid[2]);
+      }
     }
-  } else if (in_image) {
-    g_local[0] = grad[3 * p]; g_local[1] = grad[3 * p + 1]; g_local[2] = grad[3 * p + 2];
+  } else {
+    if (in_image) { g_local[0] = grad[3 * p]; g_local[1] = grad[3 * p + 1]; g_local[2] = grad[3 * p + 2]; }
+    if (id >= 0) {
+      const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
+      pv0 = __ldg(v4 + vid[0]); pv1 = __ldg(v4 + vid[1]); pv2 = __ldg(v4 + vid[2]);
+    }
   }
 
   if (id >= 0) {
     PixelGrad pg;
-    const float *verts_b = verts + (size_t)b * V * 4;
-    const float *attrs_b = FUSED ? attrs + (size_t)b * V * A : nullptr;
-    pixel_grad<FUSED>(verts_b, attrs_b, tris, id, bp, g_local, A, pg);
+    pixel_grad_loaded<FUSED>(vid, pv0, pv1, pv2, attrs_b, bp, g_local, A, pg);
     float *row = rows + lane * STRIDE;
 #pragma unroll
     for (int k = 0; k < 9; ++k) row[k] = pg.terms[k];

@@ -181,24 +181,25 @@ __device__ __forceinline__ int warp_inclusive_scan(int v) {
 // aligned rows and a full-width block; otherwise scalars.  N is a compile-time constant so that the
 // row/column split is a multiply-shift, not a division.
 template <int N>
-__device__ __forceinline__ void store_block_rows(const float *stage, float *dst_row0, size_t row_stride,
+__device__ __forceinline__ void store_block_rows(const float *stage, float *dst_row0, int row_stride,
                                                  int cols, int rows, bool vec_ok) {
   const int lane = threadIdx.x & 31;
   constexpr int run = 8 * N;                           // floats per full block row
   if (vec_ok && cols == 8) {
-    constexpr int v4_per_row = 2 * N;
+    constexpr int v4_per_row = 2 * N, total = 4 * v4_per_row;
+    const float4 *stage4 = reinterpret_cast<const float4 *>(stage);     // rows are back to back
 #pragma unroll
-    for (int k0 = 0; k0 < 4 * v4_per_row; k0 += 32) {
-      const int k = k0 + lane;
-      const int r = k / v4_per_row, c = k % v4_per_row;
-      if (k < 4 * v4_per_row && r < rows)
-        reinterpret_cast<float4 *>(dst_row0 + r * row_stride)[c] = reinterpret_cast<const float4 *>(stage + r * run)[c];
+    for (int i = 0; i < (total + 31) / 32; ++i) {
+      const int k = lane + 32 * i;
+      const int r = k / v4_per_row, c = k - r * v4_per_row;
+      if (k < total && r < rows)
+        *reinterpret_cast<float4 *>(dst_row0 + (r * row_stride + 4 * c)) = stage4[k];
     }
   } else {
     const int live = cols * N;
     for (int k = lane; k < rows * run; k += 32) {
-      const int r = k / run, c = k % run;
-      if (c < live) dst_row0[r * row_stride + c] = stage[r * run + c];
+      const int r = k / run, c = k - r * run;
+      if (c < live) dst_row0[r * row_stride + c] = stage[k];
     }
   }
 }
@@ -238,9 +239,9 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
   stage[64 + 3 * lane + 1] = best.b1;
   stage[64 + 3 * lane + 2] = best.b2;
   __syncwarp();
-  store_block_rows<1>(stage, reinterpret_cast<float *>(out_ids) + p0, (size_t)W, cols, rows, vec_ok);
-  store_block_rows<1>(stage + 32, out_z + p0, (size_t)W, cols, rows, vec_ok);
-  store_block_rows<3>(stage + 64, out_bary + 3 * p0, (size_t)W * 3, cols, rows, vec_ok);
+  store_block_rows<1>(stage, reinterpret_cast<float *>(out_ids) + p0, W, cols, rows, vec_ok);
+  store_block_rows<1>(stage + 32, out_z + p0, W, cols, rows, vec_ok);
+  store_block_rows<3>(stage + 64, out_bary + 3 * p0, W * 3, cols, rows, vec_ok);
   __syncwarp();
   if (out_image == nullptr) return;
 
@@ -268,7 +269,7 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
   }
   if (staged) {
     __syncwarp();
-    store_block_rows<(A_STATIC > 0 ? A_STATIC : 1)>(stage, out_image + p0 * A, (size_t)W * A, cols, rows, vec_ok);
+    store_block_rows<(A_STATIC > 0 ? A_STATIC : 1)>(stage, out_image + p0 * A, W * A, cols, rows, vec_ok);
   }
 }
 
@@ -490,7 +491,7 @@ struct ScatterWarpSmem {
   float4 r0[32], r1[32], r2[32], r3[32];     // setup records of the warp's 32 triangles (planes as in TileSmem)
   int2 origin[32];                           // left, bottom of each triangle's pixel box
   unsigned short segs[kScatterSegCap];       // slot | dy << 5 | dx << 9 | width << 13
-  unsigned short hits[128];                  // slot | dy << 5 | x offset << 9
+  unsigned short hits[160];                  // queue of inside pixels: slot | dy << 5 | x offset << 9
 };
 
 __global__ void __launch_bounds__(kScatterWarps * 32)
@@ -534,7 +535,28 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
   int *counts = tile_counts + (size_t)b * tiles_per_image;
   for_each_tile(big_box, tiles_x, [&](int tile, int) { atomicAdd(counts + tile, 1); });
 
+  // pass 2 of the scatter: barycentrics / depth of queued inside pixels, depth resolve by packed
+  // atomicMin in global memory (L2).  Lane h of the warp takes queue entry first + h.
+  auto shade_hits = [&](int first, int count) {
+    if (lane < count) {
+      const unsigned hit = sm.hits[first + lane];
+      const int j = hit & 31u, dy = (hit >> 5) & 15u, xo = hit >> 9;
+      const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j], q3 = sm.r3[j];
+      const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
+      const float zc[3] = {q1.w, q2.w, q3.x};
+      const float wc[3] = {q3.y, q3.z, q3.w};
+      const int2 org = sm.origin[j];
+      const int x = org.x + xo, y = org.y + dy;
+      float e[3], esum, bc[3], z;
+      edge_values(m, __ldg(cx + x), __ldg(cy + y), e);
+      edges_inside(e, esum);
+      if (fragment_depth(e, esum, zc, wc, bc, z))
+        atomicMin(keys_b + (size_t)y * W + x, depth_key(z, __float_as_int(q0.w)));
+    }
+  };
+
   // ---- rounds: the longest prefix (in lane order) of the remaining small triangles whose segments fit
+  int queued = 0;                                       // inside pixels waiting in sm.hits (warp-uniform)
   unsigned remaining = __ballot_sync(0xffffffffu, n_seg > 0);
   while (remaining) {
     const int mine = (remaining >> lane) & 1u ? n_seg : 0;
@@ -577,36 +599,29 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
           }
         }
       }
-      // compact the inside pixels of the warp and deal them to the lanes again
+      // append the warp's inside pixels to the queue (at most 4 per lane, < 32 were waiting)
       const int mine_hits = __popc(inside);
       const int upto = warp_inclusive_scan(mine_hits);
-      const int n_hits = __shfl_sync(0xffffffffu, upto, 31);
-      int at = upto - mine_hits;
-      while (inside) {
-        const int k = __ffs(inside) - 1;
-        inside &= inside - 1;
-        sm.hits[at++] = (unsigned short)((seg & 0x1ffu) | ((((seg >> 9) & 15u) + k) << 9));
-      }
+      int at = queued + upto - mine_hits;
+      const unsigned base_bits = seg & 0x1ffu, dx0 = (seg >> 9) & 15u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (inside & (1u << k)) sm.hits[at++] = (unsigned short)(base_bits | ((dx0 + k) << 9));
+      queued += __shfl_sync(0xffffffffu, upto, 31);
       __syncwarp();
-      // pass 2: barycentrics / depth for exactly those pixels, depth resolve by packed atomicMin (L2)
-      for (int h = lane; h < n_hits; h += 32) {
-        const unsigned hit = sm.hits[h];
-        const int j = hit & 31u, dy = (hit >> 5) & 15u, xo = hit >> 9;
-        const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j], q3 = sm.r3[j];
-        const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
-        const float zc[3] = {q1.w, q2.w, q3.x};
-        const float wc[3] = {q3.y, q3.z, q3.w};
-        const int2 org = sm.origin[j];
-        const int x = org.x + xo, y = org.y + dy;
-        float e[3], esum, bc[3], z;
-        edge_values(m, __ldg(cx + x), __ldg(cy + y), e);
-        edges_inside(e, esum);
-        if (fragment_depth(e, esum, zc, wc, bc, z))
-          atomicMin(keys_b + (size_t)y * W + x, depth_key(z, __float_as_int(q0.w)));
-      }
+      // shade full warps of queued pixels; keep the remainder (< 32) for the next round
+      int first = 0;
+      for (; queued - first >= 32; first += 32) shade_hits(first, 32);
+      const int left = queued - first;
+      unsigned short carry = 0;
+      if (first > 0 && lane < left) carry = sm.hits[first + lane];
+      __syncwarp();
+      if (first > 0 && lane < left) sm.hits[lane] = carry;
+      queued = left;
       __syncwarp();
     }
   }
+  shade_hits(0, queued);                                // final partial warp of pixels
 }
 
 // ---------------------------------------------------------------------------------------------
