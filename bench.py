@@ -276,9 +276,17 @@ def main():
     dom_bytes = kernel_bytes[dominant]
     achieved = dom_bytes / (stage_ms[dominant] * 1e-3) / 1e9 if stage_ms[dominant] > 0 else 0.0
     fwd_ms = per_step["bin"] + per_step["scatter"] + per_step["raster"] + per_step["resolve"]
+    traffic = None     # DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01", "dram_traffic.json")) as f:
+            t_ = json.load(f).get(args.config, {}).get(dominant)
+        if t_ and args.batch is None:
+            traffic = int((t_["dram_read_mb"] + t_["dram_write_mb"]) * 1e6)
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "hbm", "kernel": kernel_names[dominant],
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": stage_ms[dominant],
         "stages_ms_per_step": per_step,
         "forward": {"algorithmic_bytes": bytes_fwd, "ms": fwd_ms,
