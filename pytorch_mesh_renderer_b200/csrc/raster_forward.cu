@@ -35,18 +35,6 @@ namespace pmr {
 // Binning
 // ---------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ void load_triangle(const float *__restrict__ verts_b,
-                                              const int32_t *__restrict__ tris, int t,
-                                              float4 &a, float4 &b, float4 &c) {
-  const int i0 = __ldg(tris + 3 * (size_t)t + 0);
-  const int i1 = __ldg(tris + 3 * (size_t)t + 1);
-  const int i2 = __ldg(tris + 3 * (size_t)t + 2);
-  const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
-  a = __ldg(v4 + i0);
-  b = __ldg(v4 + i1);
-  c = __ldg(v4 + i2);
-}
-
 // Pixel box packed as four uint16: x = left | right << 16, y = bottom | top << 16 (W, H <= 32768).
 __device__ __forceinline__ uint2 pack_box(const PixelBox &box) {
   if (box.left >= box.right || box.bottom >= box.top) return make_uint2(0u, 0u);
@@ -164,16 +152,6 @@ __device__ __forceinline__ void append_slots(bool flag, unsigned short *list, in
   if (lane == 0) base = atomicAdd(count, __popc(votes));
   base = __shfl_sync(0xffffffffu, base, 0);
   if (flag) list[base + __popc(votes & ((1u << lane) - 1u))] = (unsigned short)threadIdx.x;
-}
-
-__device__ __forceinline__ int warp_inclusive_scan(int v) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int up = __shfl_up_sync(0xffffffffu, v, d);
-    if (lane >= d) v += up;
-  }
-  return v;
 }
 
 // Writes N floats per pixel of the warp's 8x4 block from the shared staging area (`stage`: 4 rows x
