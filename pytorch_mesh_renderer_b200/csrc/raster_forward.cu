@@ -211,15 +211,17 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
   const bool vec_ok = (W & 3) == 0 &&
       (((uintptr_t)out_ids | (uintptr_t)out_z | (uintptr_t)out_bary | (uintptr_t)out_image) & 15) == 0;
   const size_t p0 = ((size_t)b * H + blk_y0) * W + blk_x0;            // first pixel of the block
-  stage[lane] = __int_as_float(id);
-  stage[32 + lane] = best.z;
-  stage[64 + 3 * lane + 0] = best.b0;
-  stage[64 + 3 * lane + 1] = best.b1;
-  stage[64 + 3 * lane + 2] = best.b2;
+  // ids and z: a block row is 8 consecutive 4-byte values = one full 32-byte sector per row already
+  if ((lane & 7) < cols && (lane >> 3) < rows) {
+    const size_t p = p0 + (size_t)(lane >> 3) * W + (lane & 7);
+    out_ids[p] = id;
+    out_z[p] = best.z;
+  }
+  stage[3 * lane + 0] = best.b0;
+  stage[3 * lane + 1] = best.b1;
+  stage[3 * lane + 2] = best.b2;
   __syncwarp();
-  store_block_rows<1>(stage, reinterpret_cast<float *>(out_ids) + p0, W, cols, rows, vec_ok);
-  store_block_rows<1>(stage + 32, out_z + p0, W, cols, rows, vec_ok);
-  store_block_rows<3>(stage + 64, out_bary + 3 * p0, W * 3, cols, rows, vec_ok);
+  store_block_rows<3>(stage, out_bary + 3 * p0, W * 3, cols, rows, vec_ok);
   __syncwarp();
   if (out_image == nullptr) return;
 
