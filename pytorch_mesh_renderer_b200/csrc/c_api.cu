@@ -131,6 +131,9 @@ void pmr_destroy(pmr_context *ctx) {
   ctx->keys.release();
   ctx->centers.release();
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+  if (ctx->call_begin) cudaEventDestroy(ctx->call_begin);
   for (const pmr::StageInterval &iv : ctx->intervals) { cudaEventDestroy(iv.begin); cudaEventDestroy(iv.end); }
   for (cudaEvent_t e : ctx->spare_events) cudaEventDestroy(e);
   delete ctx;
@@ -278,14 +281,29 @@ int pmr_rasterize_clip_space_host(pmr_context *ctx, const float *vertices, const
   PMR_CUDA(ctx, cudaMemcpyAsync(d_a, attributes, n_a, cudaMemcpyHostToDevice, stream));
   if (n_t) PMR_CUDA(ctx, cudaMemcpyAsync(d_t, triangles, n_t, cudaMemcpyHostToDevice, stream));
   PMR_CUDA(ctx, cudaMemcpyAsync(d_bg, background, n_bg, cudaMemcpyHostToDevice, stream));
-  if (bwd) PMR_CUDA(ctx, cudaMemcpyAsync(d_g, grad_image, n_img, cudaMemcpyHostToDevice, stream));
+  // The image gradient (the largest input) is uploaded on a second stream, enqueued AFTER the small
+  // uploads (the host-to-device copy engine is a FIFO), so that it overlaps the forward pass and the
+  // download of the image (PCIe is full duplex).
+  if (bwd) {
+    if (!ctx->copy_stream) {
+      PMR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      PMR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+      PMR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->call_begin, cudaEventDisableTiming));
+    }
+    PMR_CUDA(ctx, cudaEventRecord(ctx->call_begin, stream));               // staging area free from here on
+    PMR_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->call_begin, 0));
+    PMR_CUDA(ctx, cudaMemcpyAsync(d_g, grad_image, n_img, cudaMemcpyHostToDevice, ctx->copy_stream));
+    PMR_CUDA(ctx, cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+  }
   rc = pmr::forward_impl(ctx, d_v, d_t, B, V, T, W, H, d_ids, d_bary, d_z, d_a, d_bg, A, d_img, stream);
   if (rc) return rc;
+  // the image download (device -> host) overlaps the gradient upload (host -> device)
   PMR_CUDA(ctx, cudaMemcpyAsync(image, d_img, n_img, cudaMemcpyDeviceToHost, stream));
   if (ids) PMR_CUDA(ctx, cudaMemcpyAsync(ids, d_ids, n_ids, cudaMemcpyDeviceToHost, stream));
   if (bary) PMR_CUDA(ctx, cudaMemcpyAsync(bary, d_bary, n_bary, cudaMemcpyDeviceToHost, stream));
   if (z) PMR_CUDA(ctx, cudaMemcpyAsync(z, d_z, n_ids, cudaMemcpyDeviceToHost, stream));
   if (bwd) {
+    PMR_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->copy_done, 0));
     rc = pmr::backward_impl(ctx, nullptr, d_g, d_v, d_a, d_t, d_ids, d_bary, B, V, T, A, W, H,
                             d_vertices ? d_dv : nullptr, d_attributes ? d_da : nullptr, mode, stream);
     if (rc) return rc;

@@ -39,6 +39,8 @@ struct Context {
   Buffer bins, lists, scratch, keys, centers;
   int centers_w = -1, centers_h = -1;  // image size the pixel-centre table was built for
   unsigned long long *mailbox = nullptr;   // pinned host word for the tile-list length
+  cudaStream_t copy_stream = nullptr;       // host entry point: uploads the image gradient while the forward runs
+  cudaEvent_t copy_done = nullptr, call_begin = nullptr;
   unsigned long long last_bin_entries = 0;
   long long launches = 0;             // kernels launched through this context (bench gpu_launches)
   char error[512] = {0};
