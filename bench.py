@@ -189,7 +189,7 @@ def main():
         # Weak scaling: the job renders world * B views of ONE mesh; this rank owns a contiguous slice.
         from pytorch_mesh_renderer_b200 import distributed as D
         from pytorch_mesh_renderer_b200 import synthetic as S
-        from pytorch_mesh_renderer_b200.camera_utils import transform_homogeneous
+        from pytorch_mesh_renderer_b200.camera_utils import transform_shared_mesh
         B_local = sc["clip_vertices"].shape[0]
         mine = D.shard_views(B_local * world, rank, world)
         sc["camera_matrices"] = S.orbit_cameras(B_local * world)[mine.start:mine.stop]
@@ -212,7 +212,7 @@ def main():
             # multi-view fitting: the world-space mesh is the shared parameter; d(clip) flows back
             # through the view matrices and the broadcast, then ONE all-reduce of [V,3] over NVLink.
             wv = world_vertices.detach().requires_grad_(True)
-            cv = transform_homogeneous(mvp, wv.unsqueeze(0).expand(B, -1, -1))
+            cv = transform_shared_mesh(mvp, wv)          # one kernel; its backward sums over the local views
             out = pmr.rasterize_clip_space(cv, at, tris, W, H, bg)
             out.backward(grad)
             D.all_reduce_gradients([wv.grad])

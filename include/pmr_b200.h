@@ -154,6 +154,18 @@ PMR_API int pmr_rasterize_clip_space_host(pmr_context *ctx, const float *vertice
                                   float *image, float *d_vertices, float *d_attributes,
                                   int32_t *ids, float *bary, float *z, int mode, void *stream);
 
+/*
+ * Vertex stage in front of the path: world -> clip space, clip[b][v] = M_b * (x, y, z, 1)
+ * (reference src/common/camera_utils.py:142-170 transform_homogeneous), and its backward with respect to
+ * the vertices.  matrices float32 [B,4,4] row-major; `shared` != 0: world_vertices is ONE mesh [V,3] seen
+ * by all B views and d_world [V,3] receives the gradient summed over the views (the buffer that the
+ * multi-GPU path all-reduces); `shared` == 0: world_vertices / d_world are [B,V,3].
+ */
+PMR_API int pmr_transform_forward(pmr_context *ctx, const float *matrices, const float *world_vertices,
+                                  int B, int V, int shared, float *clip_vertices, void *stream);
+PMR_API int pmr_transform_backward(pmr_context *ctx, const float *matrices, const float *d_clip_vertices,
+                                   int B, int V, int shared, float *d_world_vertices, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,8 @@ _PROTOTYPES = {
                                                          _vp, _vp, _vp, _vp, _vp]),
     "pmr_rasterize_interpolate_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                                                           _vp, _vp, _i, _vp]),
+    "pmr_transform_forward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "pmr_transform_backward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "pmr_rasterize_clip_space_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                                                      _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
 }

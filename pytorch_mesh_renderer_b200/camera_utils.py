@@ -1,19 +1,67 @@
 """Device-aware counterpart of the one camera helper on the hot path's doorstep:
-transform_homogeneous (reference src/common/camera_utils.py:142-170), which the reference
-allocates on the CPU regardless of its inputs."""
+transform_homogeneous (reference src/common/camera_utils.py:142-170), which the reference allocates on
+the CPU regardless of its inputs.  World -> clip space runs in one CUDA kernel
+(csrc/vertex_stage.cu); its backward sums the per-view clip-space gradients of a shared mesh on the
+fly, which is the on-device reduction the multi-GPU path all-reduces afterwards."""
 import torch
+
+from . import ops
+
+
+class _TransformVertices(torch.autograd.Function):
+    """matrices [B,4,4] x vertices ([V,3] shared by all views, or [B,V,3]) -> clip [B,V,4]."""
+
+    @staticmethod
+    def forward(ctx, matrices, vertices):
+        shared = vertices.dim() == 2
+        ctx.save_for_backward(matrices, vertices)
+        ctx.shared = shared
+        return ops.transform_forward(matrices, vertices, shared)
+
+    @staticmethod
+    def backward(ctx, d_clip):
+        matrices, vertices = ctx.saved_tensors
+        d_matrices = d_vertices = None
+        if ctx.needs_input_grad[1]:
+            d_vertices = ops.transform_backward(matrices, d_clip.contiguous(), ctx.shared)
+        if ctx.needs_input_grad[0]:
+            # camera fitting (reference example4): d M_b = sum_v d_clip[b,v] (x) (x, y, z, 1); off the hot path
+            w = vertices.unsqueeze(0).expand(matrices.shape[0], -1, -1) if ctx.shared else vertices
+            hom = torch.cat([w, torch.ones_like(w[..., :1])], 2)
+            d_matrices = torch.einsum("bvi,bvj->bij", d_clip, hom)
+        return d_matrices, d_vertices
+
+
+def _on_device(*tensors):
+    for t in tensors:
+        if t.is_cuda:
+            return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("pytorch_mesh_renderer_b200 needs a CUDA device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
 
 
 def transform_homogeneous(matrices, vertices):
     """Applies batched 4x4 homogeneous transforms to xyz vertices: (M V^T)^T with w = 1.
 
     matrices [B,4,4], vertices [B,N,3] -> [B,N,4].  Raises ValueError on wrong rank like
-    camera_utils.py:159-164.
+    camera_utils.py:159-164.  CPU tensors are processed on the current CUDA device and returned
+    on the CPU.
     """
     if len(matrices.shape) != 3:
         raise ValueError("matrices must have 3 dimensions (missing batch dimension?)")
     if len(vertices.shape) != 3:
         raise ValueError("vertices must have 3 dimensions (missing batch dimension?)")
-    ones = torch.ones([vertices.shape[0], vertices.shape[1], 1], dtype=torch.float32, device=vertices.device)
-    homogeneous = torch.cat([vertices, ones], 2)
-    return torch.matmul(homogeneous, matrices.to(vertices.device).transpose(1, 2))
+    home = vertices.device
+    dev = _on_device(matrices, vertices)
+    out = _TransformVertices.apply(matrices.to(dev).float(), vertices.to(dev).float())
+    return out.to(home) if home != dev else out
+
+
+def transform_shared_mesh(matrices, vertices):
+    """One mesh [V,3] seen by B views: matrices [B,4,4] -> clip [B,V,4]; the gradient with respect to
+    `vertices` comes back as [V,3], already summed over the views."""
+    if len(matrices.shape) != 3 or len(vertices.shape) != 2:
+        raise ValueError("expected matrices [B,4,4] and vertices [V,3]")
+    dev = _on_device(matrices, vertices)
+    return _TransformVertices.apply(matrices.to(dev).float(), vertices.to(dev).float())

@@ -314,4 +314,27 @@ int pmr_rasterize_clip_space_host(pmr_context *ctx, const float *vertices, const
   return PMR_OK;
 }
 
+int pmr_transform_forward(pmr_context *ctx, const float *matrices, const float *world_vertices, int B, int V,
+                          int shared, float *clip_vertices, void *stream) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (B < 0 || V < 0) return set_error(ctx, PMR_ERR_INVALID, "negative batch/vertex count");
+  if (B == 0 || V == 0) return PMR_OK;
+  if (!matrices || !world_vertices || !clip_vertices) return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(clip_vertices)) return set_error(ctx, PMR_ERR_INVALID, "clip_vertices must be 16-byte aligned");
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  return pmr::transform_forward_impl(ctx, matrices, world_vertices, B, V, shared, clip_vertices, (cudaStream_t)stream);
+}
+
+int pmr_transform_backward(pmr_context *ctx, const float *matrices, const float *d_clip_vertices, int B, int V,
+                           int shared, float *d_world_vertices, void *stream) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (B < 0 || V < 0) return set_error(ctx, PMR_ERR_INVALID, "negative batch/vertex count");
+  if (B == 0 || V == 0) return PMR_OK;
+  if (!matrices || !d_clip_vertices || !d_world_vertices) return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(d_clip_vertices)) return set_error(ctx, PMR_ERR_INVALID, "d_clip_vertices must be 16-byte aligned");
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  return pmr::transform_backward_impl(ctx, matrices, d_clip_vertices, B, V, shared, d_world_vertices,
+                                      (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -84,4 +84,10 @@ int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, 
                   int B, int V, int T, int A, int W, int H, float *d_verts, float *d_attrs, int mode,
                   cudaStream_t stream);
 
+// vertex_stage.cu
+int transform_forward_impl(Context *ctx, const float *matrices, const float *world, int B, int V, int shared,
+                           float *clip, cudaStream_t stream);
+int transform_backward_impl(Context *ctx, const float *matrices, const float *d_clip, int B, int V, int shared,
+                            float *d_world, cudaStream_t stream);
+
 }  // namespace pmr

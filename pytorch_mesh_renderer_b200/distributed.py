@@ -59,8 +59,9 @@ def rasterize_shared_mesh(world_vertices, attributes, triangles, camera_matrices
     [B_local,H,W,A].  After `loss.backward()`, `world_vertices.grad` / `attributes.grad` hold this
     rank's partial sums; `all_reduce_gradients([...])` completes them.
     """
-    from .rasterize import rasterize
+    from .camera_utils import transform_shared_mesh
+    from .rasterize import rasterize_clip_space
     B = camera_matrices.shape[0]
-    verts = world_vertices.unsqueeze(0).expand(B, -1, -1)
+    clip = transform_shared_mesh(camera_matrices, world_vertices)      # one kernel; backward sums over views
     attrs = attributes.unsqueeze(0).expand(B, -1, -1)
-    return rasterize(verts, attrs, triangles, camera_matrices, image_width, image_height, background_value)
+    return rasterize_clip_space(clip, attrs, triangles, image_width, image_height, background_value)

@@ -132,3 +132,32 @@ def rasterize_interpolate_backward(grad_image, vertices, attributes, triangles, 
             B, V, t.shape[0], A, W, H, _lib.ptr(dv), _lib.ptr(da), mode_code(mode), _lib.stream_ptr(dev))
     _lib.check(ctx, rc)
     return dv, da
+
+
+def transform_forward(matrices, vertices, shared):
+    """clip[b][v] = M_b (x, y, z, 1): matrices [B,4,4], vertices [V,3] (shared) or [B,V,3] -> [B,V,4]."""
+    m = _require(matrices, torch.float32, "matrices")
+    w = _require(vertices, torch.float32, "vertices")
+    B = m.shape[0]
+    V = w.shape[0] if shared else w.shape[1]
+    clip = torch.empty((B, V, 4), dtype=torch.float32, device=m.device)
+    ctx = _lib.context(m.device.index)
+    with torch.cuda.device(m.device):
+        rc = _lib.load().pmr_transform_forward(ctx, _lib.ptr(m), _lib.ptr(w), B, V, int(bool(shared)), _lib.ptr(clip),
+                                               _lib.stream_ptr(m.device))
+    _lib.check(ctx, rc)
+    return clip
+
+
+def transform_backward(matrices, d_clip, shared):
+    """Gradient of transform_forward with respect to the vertices: [V,3] (summed over views) or [B,V,3]."""
+    m = _require(matrices, torch.float32, "matrices")
+    g = _aligned(_require(d_clip, torch.float32, "d_clip_vertices"))
+    B, V, _ = g.shape
+    out = torch.empty((V, 3) if shared else (B, V, 3), dtype=torch.float32, device=m.device)
+    ctx = _lib.context(m.device.index)
+    with torch.cuda.device(m.device):
+        rc = _lib.load().pmr_transform_backward(ctx, _lib.ptr(m), _lib.ptr(g), B, V, int(bool(shared)), _lib.ptr(out),
+                                                _lib.stream_ptr(m.device))
+    _lib.check(ctx, rc)
+    return out

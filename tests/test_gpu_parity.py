@@ -260,3 +260,35 @@ def test_c_abi_host_entry_point(pmr, oracle):
     assert rc == 0, L.pmr_last_error(ctx)
     assert_bits(ids, c["ids"], "ids"); assert_bits(out, c["out"], "out")
     assert_bits(dv, c["d_clip_vertices"], "d_clip_vertices"); assert_bits(da, c["d_attributes"], "d_attributes")
+
+
+def test_vertex_stage_transform(pmr):
+    """transform_homogeneous / transform_shared_mesh (camera_utils.py:142-170) against torch fp32 matmul."""
+    from pytorch_mesh_renderer_b200 import camera_utils as cu
+    from pytorch_mesh_renderer_b200 import synthetic as S
+    rng = np.random.default_rng(3)
+    B, V = 5, 1000
+    m = dev(S.orbit_cameras(B)).requires_grad_(True)
+    w = dev(rng.standard_normal((V, 3)).astype(np.float32)).requires_grad_(True)
+    g = dev(rng.standard_normal((B, V, 4)).astype(np.float32))
+    hom = torch.cat([w, torch.ones_like(w[:, :1])], 1)
+    ref = torch.matmul(hom.unsqueeze(0).expand(B, -1, -1), m.transpose(1, 2))
+    ref.backward(g)
+    ref_dw, ref_dm = w.grad.clone(), m.grad.clone()
+    w.grad = None; m.grad = None
+    out = cu.transform_shared_mesh(m, w)
+    out.backward(g)
+    assert_close_t(out, ref, 1e-5); assert_close_t(w.grad, ref_dw, 1e-4); assert_close_t(m.grad, ref_dm, 1e-4)
+    w3 = w.detach().unsqueeze(0).expand(B, -1, -1).contiguous().requires_grad_(True)
+    out3 = cu.transform_homogeneous(m.detach(), w3)
+    out3.backward(g)
+    assert_close_t(out3, ref, 1e-5)
+    assert_close_t(w3.grad.sum(0), ref_dw, 1e-4)
+    out_cpu = cu.transform_homogeneous(m.detach().cpu(), w3.detach().cpu())
+    assert out_cpu.device.type == "cpu" and out_cpu.shape == (B, V, 4)
+
+
+def assert_close_t(a, b, tol):
+    a, b = a.detach().float().cpu().numpy(), b.detach().float().cpu().numpy()
+    scale = np.abs(b).max() + 1e-30
+    assert np.abs(a - b).max() <= tol * scale, (np.abs(a - b).max(), scale)
