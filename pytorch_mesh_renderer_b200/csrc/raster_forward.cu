@@ -131,6 +131,7 @@ struct TileSmem {
   float4 r2[kChunk];   // m6 m7 m8 | z1
   float4 r3[kChunk];   // z2 | w0 w1 w2
   int4 box[kChunk];    // the triangle's pixel box: left right bottom top
+  float zlo[kChunk];   // conservative lower bound of the triangle's depth (-inf unless all w > 0)
   unsigned long long key[kTilePixels];   // packed (depth, ~id) minimum per pixel (small-triangle path)
   unsigned segs[kWarps][kWarpSegCap];    // per warp: slot | row << 8 | first column << 12 | width << 16
   unsigned short hits[kWarps][128];      // per warp: inside pixels of 32 segments (slot << 8 | pixel)
@@ -293,6 +294,16 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
   fragment_clear(best);
   __syncthreads();         // publishes key / cx / cy / n_big
   const float px = sm.cx[lx], py = sm.cy[ly];
+  // pixel-centre range of this warp's 8x4 block (for the conservative edge test of the big path)
+  const float blk_px0 = sm.cx[(warp & 1) * 8], blk_px1 = sm.cx[(warp & 1) * 8 + 7];
+  const float blk_py0 = sm.cy[(warp >> 1) * 4], blk_py1 = sm.cy[(warp >> 1) * 4 + 3];
+  const float blk_pxabs = fmaxf(fabsf(blk_px0), fabsf(blk_px1)), blk_pyabs = fmaxf(fabsf(blk_py0), fabsf(blk_py1));
+  if (keys_out != nullptr && ix < W && iy < H) {
+    // binned pipeline: start from what the small triangles already drew (depth and id are all the
+    // depth rule needs; barycentrics are not produced in this mode)
+    const unsigned long long seen = keys_out[((size_t)b * H + iy) * W + ix];
+    if (seen != kEmptyKey) { best.z = ordered_to_float((unsigned)(seen >> 32)); best.id = depth_key_id(seen); }
+  }
 
   for (int base = 0; base < n_list; base += kChunk) {
     const int n_here = min(kChunk, n_list - base);
@@ -325,6 +336,17 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
       sm.r2[threadIdx.x] = make_float4(m[6], m[7], m[8], p1.z);
       sm.r3[threadIdx.x] = make_float4(p2.z, p0.w, p1.w, p2.w);
       sm.box[threadIdx.x] = bx;
+      // Depth bound for the hierarchical z test of the big path: with all w > 0 the pixel depth
+      // (b.z)/(b.w) is a positive-weight average of z_i/w_i, so it is >= min_i z_i/w_i; the computed
+      // depth differs from the exact one by < 10 ulp of max|z_i/w_i| (three rounded barycentrics, two
+      // 3-term dot products, one division), covered by the 2^-19 relative slack.
+      float zlo = -INFINITY;
+      if (p0.w > 0.0f && p1.w > 0.0f && p2.w > 0.0f) {
+        const float d0 = p0.z / p0.w, d1 = p1.z / p1.w, d2 = p2.z / p2.w;
+        const float dabs = fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fabsf(d2));
+        zlo = fminf(fminf(d0, d1), d2) - dabs * 1.9073486e-6f - 1e-30f;
+      }
+      sm.zlo[threadIdx.x] = zlo;
       // the box inside this tile, in tile-local pixel coordinates
       x0 = max(bx.x, tile_x0) - tile_x0; x1 = min(bx.y, tile_x0 + kTileW) - tile_x0;
       y0 = max(bx.z, tile_y0) - tile_y0; y1 = min(bx.w, tile_y0 + kTileH) - tile_y0;
@@ -405,10 +427,29 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
     __syncthreads();
     const int n_big = sm.n_big;
     for (int g0 = 0; g0 < n_big; g0 += 32) {
+      // Farthest depth any pixel of this warp's block currently holds (1.0 while a pixel is empty):
+      // a triangle whose depth bound lies beyond it cannot change the block (K.cpp:401 rejects z > zbuf).
+      const float block_zmax = ordered_to_float(__reduce_max_sync(0xffffffffu, float_to_ordered(best.z)));
       bool touches = false;
       if (g0 + lane < n_big) {
-        const int4 bx = sm.box[sm.big_list[g0 + lane]];
-        touches = bx.x < blk_x0 + 8 && bx.y > blk_x0 && bx.z < blk_y0 + 4 && bx.w > blk_y0;
+        const int jj = sm.big_list[g0 + lane];
+        const int4 bx = sm.box[jj];
+        touches = bx.x < blk_x0 + 8 && bx.y > blk_x0 && bx.z < blk_y0 + 4 && bx.w > blk_y0 &&
+                  sm.zlo[jj] <= block_zmax;
+        if (touches) {
+          // Conservative edge test: an edge function is linear, so its largest exact value over the
+          // block's pixel centres sits at a corner; the fp32 evaluation at any pixel is within
+          // 3 ulp-sums of it, the corner evaluation too.  If even that bound is negative for one edge,
+          // no pixel of the block can pass the inside test (K.cpp:93-98).
+          const float4 q0 = sm.r0[jj], q1 = sm.r1[jj], q2 = sm.r2[jj];
+          const float ea[3] = {q0.x, q1.x, q2.x}, eb[3] = {q0.y, q1.y, q2.y}, ec[3] = {q0.z, q1.z, q2.z};
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float hi = ea[i] * (ea[i] >= 0.0f ? blk_px1 : blk_px0) + eb[i] * (eb[i] >= 0.0f ? blk_py1 : blk_py0) + ec[i];
+            const float mag = fabsf(ea[i]) * blk_pxabs + fabsf(eb[i]) * blk_pyabs + fabsf(ec[i]);
+            if (hi < -9.5367432e-7f * mag) touches = false;             // 2^-20 = 16 ulp of the magnitude sum
+          }
+        }
       }
       unsigned todo = __ballot_sync(0xffffffffu, touches);
       while (todo) {

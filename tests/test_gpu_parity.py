@@ -243,6 +243,28 @@ def test_occlusion_soup_vs_oracle(pmr, oracle):
     assert_bits(out.cpu().numpy(), ref["out"], "out")
 
 
+def test_deep_occlusion_vs_oracle(pmr, oracle):
+    """Depth complexity ~45 (1 500 large triangles, 2 x 256x256): exercises the hierarchical-z and
+    conservative edge rejection of the large-triangle path; still bit-exact, gradients included."""
+    from pytorch_mesh_renderer_b200 import synthetic as S
+    sc = S.occlusion_soup(2, 256, n_triangles=1500, scale=0.4)
+    g = S.upstream_gradient((2, 256, 256, 9), seed=3)
+    ref = oracle.rasterize_clip_space(sc["clip_vertices"], sc["attributes"], sc["triangles"], 256, 256, sc["background"],
+                                      grad_out=g)
+    cv = dev(sc["clip_vertices"]).requires_grad_(True)
+    at = dev(sc["attributes"]).requires_grad_(True)
+    with pmr.backward_mode("ordered"):
+        out, (ids, bary, z) = pmr.rasterize_clip_space(cv, at, dev(sc["triangles"]), 256, 256, dev(sc["background"]),
+                                                        return_buffers=True)
+        out.backward(dev(g))
+    assert_bits(ids.cpu().numpy(), ref["ids"], "ids")
+    assert_bits(bary.detach().cpu().numpy(), ref["bary"], "bary")
+    assert_bits(z.detach().cpu().numpy(), ref["z"], "z")
+    assert_bits(out.detach().cpu().numpy(), ref["out"], "out")
+    assert_bits(cv.grad.cpu().numpy(), ref["d_vertices"], "d_vertices")
+    assert_bits(at.grad.cpu().numpy(), ref["d_attributes"], "d_attributes")
+
+
 def test_c_abi_host_entry_point(pmr, oracle):
     """pmr_rasterize_clip_space_host with plain numpy host buffers (what bench.py times as e2e)."""
     from pytorch_mesh_renderer_b200 import _lib
