@@ -136,6 +136,7 @@ struct TileSmem {
   unsigned segs[kWarps][kWarpSegCap];    // per warp: slot | row << 8 | first column << 12 | width << 16
   unsigned short hits[kWarps][128];      // per warp: inside pixels of 32 segments (slot << 8 | pixel)
   unsigned short big_list[kChunk];
+  int depth_bucket[32], depth_cursor[32];   // front-to-back ordering of the big list (32 depth slices)
   float cx[kTileW], cy[kTileH];          // pixel-centre NDC coordinates of the tile's columns / rows
   int n_big;
 };
@@ -279,6 +280,7 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
   if (threadIdx.x < kTileW) sm.cx[threadIdx.x] = pixel_center(tile_x0 + threadIdx.x, half_w);
   else if (threadIdx.x < kTileW + kTileH) sm.cy[threadIdx.x - kTileW] = pixel_center(tile_y0 + threadIdx.x - kTileW, half_h);
   if (threadIdx.x == 0) sm.n_big = 0;
+  if (threadIdx.x < 32) { sm.depth_bucket[threadIdx.x] = 0; sm.depth_cursor[threadIdx.x] = 0; }
 
   int n_list;
   const int32_t *list = nullptr;
@@ -310,6 +312,7 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
     if (base > 0) {
       __syncthreads();     // previous chunk's records fully consumed
       if (threadIdx.x == 0) sm.n_big = 0;
+      if (threadIdx.x < 32) { sm.depth_bucket[threadIdx.x] = 0; sm.depth_cursor[threadIdx.x] = 0; }
       __syncthreads();
     }
 
@@ -372,7 +375,16 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
     int total_segs = small ? seg_end : 0;              // the fitting segments form a prefix
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) total_segs = max(total_segs, __shfl_xor_sync(0xffffffffu, total_segs, d));
-    append_slots(overlaps && !small, sm.big_list, &sm.n_big);
+    // Large triangles are walked front to back (32 slices of their depth bound), which lets the
+    // hierarchical z test of the big path reject most of what lies behind the first few layers.
+    const bool is_big = overlaps && !small;
+    int slice = 0;
+    if (is_big) {
+      const float zl = sm.zlo[threadIdx.x];
+      slice = zl > -1.0f ? min(31, (int)((zl + 1.0f) * 16.0f)) : 0;
+      atomicAdd(&sm.depth_bucket[slice], 1);
+      atomicAdd(&sm.n_big, 1);
+    }
     __syncwarp();
 
     // ---- small triangles (warp-local: no block barrier): 32 row segments per round
@@ -426,6 +438,14 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
     // ---- big triangles: warp per 8x4 block, ballot cull, lane per pixel (needs everyone's records)
     __syncthreads();
     const int n_big = sm.n_big;
+    if (n_big > 0) {
+      // exclusive prefix of the slice counts (every warp computes it for itself), then placement
+      const int count = sm.depth_bucket[lane];
+      const int start = warp_inclusive_scan(count) - count;
+      const int my_start = __shfl_sync(0xffffffffu, start, slice);
+      if (is_big) sm.big_list[my_start + atomicAdd(&sm.depth_cursor[slice], 1)] = (unsigned short)threadIdx.x;
+      __syncthreads();
+    }
     for (int g0 = 0; g0 < n_big; g0 += 32) {
       // Farthest depth any pixel of this warp's block currently holds (1.0 while a pixel is empty):
       // a triangle whose depth bound lies beyond it cannot change the block (K.cpp:401 rejects z > zbuf).
