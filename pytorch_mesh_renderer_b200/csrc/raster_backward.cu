@@ -240,7 +240,7 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
     // Stage the block's gradient rows through shared memory: a block row is 8*A contiguous
     // floats, read as float4 when the image rows keep them 16-byte aligned.
     float *stage = rows;
-    if ((W & 7) == 0) {
+    if ((W & 7) == 0 && ((uintptr_t)grad & 15) == 0) {
       constexpr int V4_PER_ROW = 2 * A;          // 8*A floats
       constexpr int N_V4 = 4 * V4_PER_ROW;
       constexpr int PER_LANE = (N_V4 + 31) / 32;
