@@ -62,48 +62,50 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs, in a separate
+    nvidia-smi process (the recipe's clocks line) so that the Python launch loop cannot starve it."""
 
-    def __init__(self, index, period=0.004):
-        super().__init__(daemon=True)
-        self.index, self.period = index, period
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._halt = threading.Event()
-        self.ok = False
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index, period_ms=10):
+        import subprocess
+        self.proc = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
-            self.ok = False
+            self.proc = None
 
-    def run(self):
-        if not self.ok:
-            return
-        nv = self.nv
-        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
-                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
-        while not self._halt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
-            except Exception:
-                pass
-            self._halt.wait(self.period)
+    def start(self):
+        time.sleep(0.05)          # let the first samples arrive before the timed region begins
 
     def stop(self):
-        self._halt.set()
-        if self.is_alive():
-            self.join(timeout=2)
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        samples, reasons, max_mhz = [], set(), None
+        if self.proc is not None:
+            time.sleep(0.02)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                out = ""
+            for line in out.splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 6:
+                    continue
+                try:
+                    samples.append(float(f[0]))
+                    max_mhz = float(f[1])
+                except ValueError:
+                    continue
+                for name, v in zip(self.NAMES, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(samples) if samples else None, "sm_max_mhz": max_mhz,
+                "reasons": sorted(reasons), "samples": len(samples)}
 
 
 def run_reference(args, rank):
