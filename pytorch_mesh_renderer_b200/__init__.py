@@ -2,10 +2,12 @@
 
 Public surface = the reference's for this path (src/mesh_renderer/__init__.py:2,
 rasterize.py, rasterize_triangles_ext.py): `rasterize`, `rasterize_clip_space`,
-`rasterize_barycentric`, `BarycentricRasterizer`.  Everything runs in hand-written CUDA
+`rasterize_barycentric`, `BarycentricRasterizer`, plus `render` / `tone_mapper` (the package exports of
+src/mesh_renderer/__init__.py:1) as a device-aware caller.  Rasterization and interpolation run in hand-written CUDA
 (csrc/, built into libpmr_b200.so for sm_100a) behind the C ABI of include/pmr_b200.h.
 """
 from .rasterize import rasterize, rasterize_barycentric, rasterize_clip_space
+from .render import phong_shader, render, tone_mapper
 from .rasterize_triangles_ext import (BarycentricRasterizer, RasterizeInterpolate, backward_mode,
                                       get_backward_mode, set_backward_mode)
 

@@ -65,3 +65,55 @@ def transform_shared_mesh(matrices, vertices):
         raise ValueError("expected matrices [B,4,4] and vertices [V,3]")
     dev = _on_device(matrices, vertices)
     return _TransformVertices.apply(matrices.to(dev).float(), vertices.to(dev).float())
+
+
+# ---------------------------------------------------------------------------------------------
+# Camera builders (reference src/common/camera_utils.py:10-139), device-aware: every tensor is
+# created on the device of the inputs, no numpy round trips, no host synchronisation.
+# ---------------------------------------------------------------------------------------------
+
+def euler_matrices(angles):
+    """XYZ Tait-Bryan rotations, [N,3] angles in radians -> [N,4,4] (camera_utils.py:10-42)."""
+    sx, sy, sz = torch.sin(angles).unbind(1)
+    cx, cy, cz = torch.cos(angles).unbind(1)
+    zero, one = torch.zeros_like(sx), torch.ones_like(sx)
+    rows = [cz * cy, cz * sy * sx - cx * sz, sz * sx + cz * cx * sy, zero,
+            cy * sz, cz * cx + sz * sy * sx, cx * sz * sy - cz * sx, zero,
+            -sy, cy * sx, cy * cx, zero,
+            zero, zero, zero, one]
+    return torch.stack(rows, 1).reshape(-1, 4, 4)
+
+
+def look_at(eye, center, world_up):
+    """gluLookAt: world -> eye space matrices [N,4,4] from [N,3] eye, gaze target and up vector
+    (camera_utils.py:45-96).  Degenerate inputs (eye == center, up parallel to the gaze) raise
+    ValueError; the check costs one device-to-host read, like the reference's numpy asserts."""
+    forward = center - eye
+    forward_norm = torch.linalg.norm(forward, dim=1, keepdim=True)
+    side = torch.cross(forward / forward_norm, world_up, dim=-1)
+    side_norm = torch.linalg.norm(side, dim=1, keepdim=True)
+    if bool((forward_norm <= 1e-6).any()) or bool((side_norm <= 1e-6).any()):
+        raise ValueError("Camera matrix is degenerate (eye and center coincide, or up is parallel to the gaze).")
+    forward = forward / forward_norm
+    side = side / side_norm
+    up = torch.cross(side, forward, dim=-1)
+    rotation = torch.stack([side, up, -forward], 1)                       # [N,3,3]
+    translation = -torch.einsum("nij,nj->ni", rotation, eye)
+    top = torch.cat([rotation, translation.unsqueeze(2)], 2)               # [N,3,4]
+    bottom = torch.zeros_like(top[:, :1, :])
+    bottom[:, 0, 3] = 1.0
+    return torch.cat([top, bottom], 1)
+
+
+def perspective(aspect_ratio, fov_y, near_clip, far_clip):
+    """gluPerspective: [N] fov (degrees), near, far -> [N,4,4] (camera_utils.py:99-139)."""
+    import math
+    f = 1.0 / torch.tan(fov_y * (math.pi / 360.0))
+    depth = far_clip - near_clip
+    m = torch.zeros((fov_y.shape[0], 4, 4), dtype=torch.float32, device=fov_y.device)
+    m[:, 0, 0] = f / aspect_ratio
+    m[:, 1, 1] = f
+    m[:, 2, 2] = -(far_clip + near_clip) / depth
+    m[:, 2, 3] = -2.0 * (far_clip * near_clip / depth)
+    m[:, 3, 2] = -1.0
+    return m

@@ -1,0 +1,149 @@
+"""Direct caller of the hot path: `render` / `phong_shader` / `tone_mapper` with the signatures of the
+reference's src/mesh_renderer/render.py (render :16-228, phong_shader :231-386, tone_mapper :389-419),
+device-aware (everything stays on the device of `vertices`; the reference allocates on the CPU, SURVEY
+F11).  Rasterization and attribute interpolation run in the CUDA kernels of libpmr_b200; the Phong
+lighting here is host-side torch code (SURVEY section 8f ranks its fusion into one kernel as the next
+row) and is checked against outputs of the unmodified reference (tests/golden/render_*.npz) and the
+reference's PNG fixtures.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import camera_utils
+from .rasterize import rasterize
+
+
+def _per_image(value, batch, what, device):
+    """float | 0-D tensor | [batch] tensor -> float32 [batch] on `device` (render.py:126-146)."""
+    if isinstance(value, (int, float)):
+        return torch.full((batch,), float(value), dtype=torch.float32, device=device)
+    value = value.to(device=device, dtype=torch.float32)
+    if value.dim() == 0:
+        return value.expand(batch).clone()
+    if list(value.shape) != [batch]:
+        raise ValueError("%s must be a float, a 0D tensor, or a 1D tensor with shape [batch_size]." % what)
+    return value
+
+
+def _per_image_vec3(value, batch, what, device):
+    value = value.to(device)
+    if list(value.shape) == [3]:
+        return value.unsqueeze(0).expand(batch, 3)
+    if list(value.shape) != [batch, 3]:
+        raise ValueError("%s must have shape [batch_size, 3] or [3]." % what)
+    return value
+
+
+def render(vertices, triangles, normals, diffuse_colors, camera_position, camera_lookat, camera_up,
+           light_positions, light_intensities, image_width, image_height, specular_colors=None,
+           shininess_coefficients=None, ambient_color=None, fov_y=40.0, near_clip=0.01, far_clip=10.0):
+    """Phong-shaded render of a batch of meshes -> RGBA [batch, height, width, 4].
+
+    Arguments, shapes and ValueErrors follow render.py:16-181.  Per-vertex attributes are packed as
+    [normals, positions, diffuse(, specular(, shininess))] (A = 9 / 12 / 13), interpolated by the
+    rasterizer with background -1, then lit per pixel.
+    """
+    if vertices.dim() != 3 or vertices.shape[-1] != 3:
+        raise ValueError("Vertices must have shape [batch_size, vertex_count, 3].")
+    batch = vertices.shape[0]
+    if normals.dim() != 3 or normals.shape[-1] != 3:
+        raise ValueError("Normals must have shape [batch_size, vertex_count, 3].")
+    if light_positions.dim() != 3 or light_positions.shape[-1] != 3:
+        raise ValueError("light_positions must have shape [batch_size, light_count, 3].")
+    if light_intensities.dim() != 3 or light_intensities.shape[-1] != 3:
+        raise ValueError("light_intensities must have shape [batch_size, light_count, 3].")
+    if diffuse_colors.dim() != 3 or diffuse_colors.shape[-1] != 3:
+        raise ValueError("diffuse_colors must have shape [batch_size, vertex_count, 3].")
+    if ambient_color is not None and list(ambient_color.shape) != [batch, 3]:
+        raise ValueError("ambient_color must have shape [batch_size, 3].")
+    if (specular_colors is None) != (shininess_coefficients is None):
+        raise ValueError("Specular colors and shininess coefficients must be supplied together.")
+
+    home = vertices.device
+    device = home if home.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+    to = lambda t: t.to(device) if t is not None else None
+    vertices, normals, diffuse_colors = to(vertices), to(normals), to(diffuse_colors)
+    light_positions, light_intensities, ambient_color = to(light_positions), to(light_intensities), to(ambient_color)
+    camera_position = _per_image_vec3(camera_position, batch, "camera_position", device)
+    camera_lookat = _per_image_vec3(camera_lookat, batch, "camera_lookat", device)
+    camera_up = _per_image_vec3(camera_up, batch, "camera_up", device)
+    fov_y = _per_image(fov_y, batch, "fov_y", device)
+    near_clip = _per_image(near_clip, batch, "near_clip", device)
+    far_clip = _per_image(far_clip, batch, "far_clip", device)
+
+    attributes = [normals, vertices, diffuse_colors]
+    per_vertex_shininess = False
+    if specular_colors is not None:
+        specular_colors = to(specular_colors)
+        if isinstance(shininess_coefficients, (int, float)):
+            shininess_coefficients = torch.tensor(float(shininess_coefficients), dtype=torch.float32)
+        shininess_coefficients = to(shininess_coefficients)
+        if specular_colors.dim() != 3:
+            raise ValueError("The specular colors must have shape [batch_size, vertex_count, 3].")
+        if shininess_coefficients.dim() > 2:
+            raise ValueError("The shininess coefficients must have shape at most [batch_size, vertex_count].")
+        attributes.append(specular_colors)
+        if shininess_coefficients.dim() == 2:
+            per_vertex_shininess = True
+            attributes.append(shininess_coefficients.unsqueeze(2))
+    vertex_attributes = torch.cat(attributes, 2)
+
+    view = camera_utils.look_at(camera_position, camera_lookat, camera_up)
+    projection = camera_utils.perspective(image_width / image_height, fov_y, near_clip, far_clip)
+    clip_from_world = torch.matmul(projection, view)
+
+    background = torch.full((vertex_attributes.shape[2],), -1.0, device=device)        # render.py:197
+    pixels = rasterize(vertices, vertex_attributes, triangles.to(device), clip_from_world, image_width,
+                       image_height, background)
+
+    pixel_normals = F.normalize(pixels[..., 0:3], p=2, dim=3)
+    pixel_positions = pixels[..., 3:6]
+    pixel_diffuse = pixels[..., 6:9]
+    pixel_specular = pixel_shininess = None
+    if specular_colors is not None:
+        pixel_specular = pixels[..., 9:12]
+        pixel_shininess = pixels[..., 12] if per_vertex_shininess else shininess_coefficients.reshape(-1, 1, 1)
+    # background pixels carry diffuse = -1 in every channel (render.py:215)
+    mask = (pixel_diffuse >= 0.0).any(dim=3).to(torch.float32)
+    image = phong_shader(pixel_normals, mask, pixel_positions, light_positions, light_intensities, pixel_diffuse,
+                         camera_position if specular_colors is not None else None, pixel_specular,
+                         pixel_shininess, ambient_color)
+    return image.to(home) if home != device else image
+
+
+def phong_shader(normals, alphas, pixel_positions, light_positions, light_intensities, diffuse_colors=None,
+                 camera_position=None, specular_colors=None, shininess_coefficients=None, ambient_color=None):
+    """Per-pixel Phong lighting of rasterized buffers -> RGBA [batch, height, width, 4], flipped
+    vertically (row 0 of the result is the top of the image).  Mirrors render.py:231-386, including
+    its per-(image, light) L2 normalisation of the specular dot products over all pixels (:347-353)."""
+    batch, height, width = normals.shape[:3]
+    n = normals.reshape(batch, 1, -1, 3)                                   # [B,1,P,3]
+    pos = pixel_positions.reshape(batch, 1, -1, 3)
+    kd = diffuse_colors.reshape(batch, -1, 3)
+    to_light = F.normalize(light_positions.unsqueeze(2) - pos, p=2, dim=3)               # [B,L,P,3]
+    n_dot_l = torch.clamp((n * to_light).sum(3), 0.0, 1.0)                               # [B,L,P]
+    rgb = (kd.unsqueeze(1) * n_dot_l.unsqueeze(3) * light_intensities.unsqueeze(2)).sum(1)
+    if ambient_color is not None:
+        rgb = ambient_color.unsqueeze(1) * kd + rgb
+    if camera_position is not None:
+        ks = specular_colors.reshape(batch, -1, 3)
+        mirror = F.normalize(2.0 * n_dot_l.unsqueeze(3) * n - to_light, p=2, dim=3)
+        to_camera = F.normalize(camera_position.reshape(batch, 1, 3) - pos[:, 0], p=2, dim=2)       # [B,P,3]
+        r_dot_v = (mirror * to_camera.unsqueeze(1)).sum(3)                                         # [B,L,P]
+        r_dot_v = torch.clamp(F.normalize(r_dot_v, p=2, dim=2), 0.0, 1.0)
+        r_dot_v = torch.where(n_dot_l != 0.0, r_dot_v, torch.zeros_like(r_dot_v))
+        shininess = shininess_coefficients.unsqueeze(1)                    # broadcasts over [B,L,H,W]
+        specularity = torch.pow(r_dot_v.reshape(batch, -1, height, width), shininess).reshape(batch, -1, height * width, 1)
+        rgb = rgb + (ks.unsqueeze(1) * specularity * light_intensities.unsqueeze(2)).sum(1)
+    rgb = rgb.reshape(batch, height, width, 3)
+    alpha = alphas.reshape(batch, height, width, 1)
+    rgb = torch.where(alpha > 0.5, rgb, torch.zeros_like(rgb))
+    return torch.flip(torch.cat([rgb, alpha], 3), dims=[1])
+
+
+def tone_mapper(image, gamma):
+    """Per-image gamma correction scaled so that the image maximum becomes 1, clipped to [0, 1]
+    (render.py:389-419)."""
+    corrected = torch.pow(image, gamma)
+    peak = corrected.reshape(image.shape[0], -1).max(1).values.reshape(-1, 1, 1, 1)
+    return torch.clamp(corrected / peak, 0.0, 1.0)
