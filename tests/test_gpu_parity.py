@@ -21,10 +21,10 @@ from conftest import GOLDEN_DIR, assert_bits, golden_names, grad_from_seed, load
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-KERNEL_CASES = [n for n in golden_names() if "vertices" in np.load(os.path.join(GOLDEN_DIR, n + ".npz")).files
-                and not n.endswith("640x480")]
+KERNEL_CASES = [n for n in golden_names() if "df_dbary" in np.load(os.path.join(GOLDEN_DIR, n + ".npz")).files
+                and not n.endswith("640x480") and not n.startswith("render_")]
 FULL_CASES = [n for n in golden_names() if "clip_vertices" in np.load(os.path.join(GOLDEN_DIR, n + ".npz")).files
-              and not n.endswith("640x480")]
+              and not n.endswith("640x480") and not n.startswith("render_")]
 DIGESTS = json.load(open(os.path.join(GOLDEN_DIR, "digests.json")))
 
 
