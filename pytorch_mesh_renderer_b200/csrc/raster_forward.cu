@@ -196,15 +196,36 @@ __device__ __forceinline__ void evaluate_winner(const float4 &p0, const float4 &
   out.z = z; out.id = t; out.b0 = bc[0]; out.b1 = bc[1]; out.b2 = bc[2];
 }
 
+// One row of a block (bytes contiguous in shared and in global memory, both 16-byte aligned, size a
+// multiple of 16) handed to the bulk-copy engine: cp.async.bulk shared::cta -> global (SASS UBLKCP).
+// The issuing lane commits the group and must wait for the reads (bulk_store_wait) before the
+// shared memory is reused or the CTA exits.
+__device__ __forceinline__ void bulk_store_row(float *dst, const float *src_shared, unsigned bytes) {
+  const unsigned src = (unsigned)__cvta_generic_to_shared(src_shared);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_store_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // Output of one warp's 8x4 pixel block (lane = pixel): ids / z / barycentrics and, when requested, the
-// interpolated attributes of rast.py:118-150, transposed through `stage` (32*16 floats of shared
-// memory owned by the warp) so that global stores are whole 16-byte vectors.
+// interpolated attributes of rast.py:118-150.  ids and z rows are full 32-byte sectors as they are.
+// Barycentrics (12 B/pixel) and attributes (4A B/pixel) are transposed through `stage` (32*16 floats of
+// shared memory owned by the warp) into row-contiguous runs; full, aligned blocks are then written by
+// the bulk-copy engine (one elected lane issues one cp.async.bulk per block row: 96 B and 32*A B), which
+// takes the copy loops off the instruction-issue-bound SMs; edge / unaligned blocks use vector or
+// scalar stores.
 template <int A_STATIC>
 __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, int blk_y0, int W, int H, int V,
                                                const Fragment &best, const int32_t *__restrict__ tris,
                                                const float *__restrict__ attrs, const float *__restrict__ background,
                                                int A, int32_t *__restrict__ out_ids, float *__restrict__ out_bary,
-                                               float *__restrict__ out_z, float *__restrict__ out_image) {
+                                               float *__restrict__ out_z, float *__restrict__ out_image,
+                                               const float *corners = nullptr) {
+  // `corners`: the winner's 3*A corner attributes already in registers ([corner][attribute]), or
+  // nullptr to gather them here.
   const int lane = threadIdx.x & 31;
   const bool covered = best.id >= 0;
   const int id = covered ? best.id : 0;
@@ -213,46 +234,67 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
   const bool vec_ok = (W & 3) == 0 &&
       (((uintptr_t)out_ids | (uintptr_t)out_z | (uintptr_t)out_bary | (uintptr_t)out_image) & 15) == 0;
   const size_t p0 = ((size_t)b * H + blk_y0) * W + blk_x0;            // first pixel of the block
-  // ids and z: a block row is 8 consecutive 4-byte values = one full 32-byte sector per row already
-  if ((lane & 7) < cols && (lane >> 3) < rows) {
+  const bool in_image = (lane & 7) < cols && (lane >> 3) < rows;
+  if (in_image) {
     const size_t p = p0 + (size_t)(lane >> 3) * W + (lane & 7);
     out_ids[p] = id;
     out_z[p] = best.z;
   }
+  // staging layout: barycentrics in floats [0, 96), attributes in [96, 96 + 32*A)
+  constexpr int kImageAt = 96;
+  constexpr bool staged = A_STATIC > 0 && kImageAt + 32 * A_STATIC <= 32 * 16;
+  const bool bulk = vec_ok && cols == 8 && rows == 4 && (out_image == nullptr || staged);
   stage[3 * lane + 0] = best.b0;
   stage[3 * lane + 1] = best.b1;
   stage[3 * lane + 2] = best.b2;
-  __syncwarp();
-  store_block_rows<3>(stage, out_bary + 3 * p0, W * 3, cols, rows, vec_ok);
-  __syncwarp();
-  if (out_image == nullptr) return;
 
-  // rast.py:118-150: corner attributes weighted by barycentrics, alpha, background blend.
-  const bool staged = A_STATIC > 0 && A_STATIC <= 16;   // compiled-in attribute counts use the staging area
-  float *direct = out_image + (p0 + (size_t)(lane >> 3) * W + (lane & 7)) * A;
-  float *dst = staged ? stage + lane * A : direct;
-  const bool in_image = (lane & 7) < cols && (lane >> 3) < rows;
-  if (staged || in_image) {
-    if (!covered) {
-      for (int a = 0; a < A; ++a) dst[a] = __ldg(background + a);
-    } else {
-      const float *at = attrs + (size_t)b * V * A;
-      const float *c0 = at + (size_t)__ldg(tris + 3 * (size_t)id + 0) * A;
-      const float *c1 = at + (size_t)__ldg(tris + 3 * (size_t)id + 1) * A;
-      const float *c2 = at + (size_t)__ldg(tris + 3 * (size_t)id + 2) * A;
-      const float alpha = coverage_alpha(best.b0, best.b1, best.b2);
-      const float one_minus = 1.0f - alpha;
+  if (out_image != nullptr) {
+    // rast.py:118-150: corner attributes weighted by barycentrics, alpha, background blend.
+    float *dst = staged ? stage + kImageAt + lane * A : out_image + (p0 + (size_t)(lane >> 3) * W + (lane & 7)) * A;
+    if (staged || in_image) {
+      if (!covered) {
+        for (int a = 0; a < A; ++a) dst[a] = __ldg(background + a);
+      } else {
+        const float alpha = coverage_alpha(best.b0, best.b1, best.b2);
+        const float one_minus = 1.0f - alpha;
+        if (corners != nullptr) {
 #pragma unroll
-      for (int a = 0; a < A; ++a) {
-        const float img = __ldg(c0 + a) * best.b0 + __ldg(c1 + a) * best.b1 + __ldg(c2 + a) * best.b2;
-        dst[a] = alpha * img + one_minus * __ldg(background + a);
+          for (int a = 0; a < A; ++a) {
+            const float img = corners[a] * best.b0 + corners[A + a] * best.b1 + corners[2 * A + a] * best.b2;
+            dst[a] = alpha * img + one_minus * __ldg(background + a);
+          }
+        } else {
+          const float *at = attrs + (size_t)b * V * A;
+          const float *c0 = at + (size_t)__ldg(tris + 3 * (size_t)id + 0) * A;
+          const float *c1 = at + (size_t)__ldg(tris + 3 * (size_t)id + 1) * A;
+          const float *c2 = at + (size_t)__ldg(tris + 3 * (size_t)id + 2) * A;
+#pragma unroll
+          for (int a = 0; a < A; ++a) {
+            const float img = __ldg(c0 + a) * best.b0 + __ldg(c1 + a) * best.b1 + __ldg(c2 + a) * best.b2;
+            dst[a] = alpha * img + one_minus * __ldg(background + a);
+          }
+        }
       }
     }
   }
-  if (staged) {
+  __syncwarp();
+  if (bulk) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy reads
     __syncwarp();
-    store_block_rows<(A_STATIC > 0 ? A_STATIC : 1)>(stage, out_image + p0 * A, W * A, cols, rows, vec_ok);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        bulk_store_row(out_bary + 3 * (p0 + (size_t)r * W), stage + r * 24, 96u);
+        if (out_image != nullptr)
+          bulk_store_row(out_image + (p0 + (size_t)r * W) * A, stage + kImageAt + r * 8 * A, 32u * (unsigned)A);
+      }
+      bulk_store_commit_and_wait();
+    }
+    return;
   }
+  store_block_rows<3>(stage, out_bary + 3 * p0, W * 3, cols, rows, vec_ok);
+  if (out_image != nullptr && staged)
+    store_block_rows<(A_STATIC > 0 ? A_STATIC : 1)>(stage + kImageAt, out_image + p0 * A, W * A, cols, rows, vec_ok);
 }
 
 template <int A_STATIC>
@@ -699,6 +741,8 @@ resolve_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris
       evaluate_winner(p0, p1, p2, __ldg(centers + ix), __ldg(centers + W + iy), t, best);
     }
   }
+  // (Gathering the 3*A corner attributes here, together with the vertices, was measured: 60 registers
+  // instead of 38 cost more occupancy than the shorter dependency chain gained: 0.355 -> 0.411 ms.)
   block_epilogue<A_STATIC>(stage_all[warp], b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
                            out_ids, out_bary, out_z, out_image);
 }
