@@ -202,6 +202,7 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
   // per warp: 32 rows of NV sums + 3 vertex ids; the gradient staging area aliases the rows (it is
   // consumed into registers before the first row is written)
   __shared__ __align__(16) float rows_all[kBlockWarps][32 * STRIDE + 4];
+  __shared__ __align__(8) unsigned long long grad_ready[kBlockWarps];      // mbarriers of the bulk gradient loads
   static_assert(32 * STRIDE >= 32 * A, "gradient staging must fit the row area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,29 +242,33 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
     // floats, read as float4 when the image rows keep them 16-byte aligned.
     float *stage = rows;
     if ((W & 7) == 0 && ((uintptr_t)grad & 15) == 0) {
-      constexpr int V4_PER_ROW = 2 * A;          // 8*A floats
-      constexpr int N_V4 = 4 * V4_PER_ROW;
-      constexpr int PER_LANE = (N_V4 + 31) / 32;
-      float4 held[PER_LANE];
+      // The block's four gradient rows (8*A contiguous floats each, 16-byte aligned) are fetched by
+      // the bulk-copy engine straight into shared memory (cp.async.bulk global -> shared::cta,
+      // completion on a per-warp mbarrier; SASS UBLKCP): no registers held, no LDG/STS pairs issued
+      // by the SM, and the copy is in flight while the vertices are gathered.
       const float *block_grad = grad + (((long long)b * H + y0) * W + x0) * A;   // first pixel of the block
-#pragma unroll
-      for (int i = 0; i < PER_LANE; ++i) {
-        const int k = lane + 32 * i;
-        const int r = k / V4_PER_ROW, c = k - r * V4_PER_ROW;
-        if (k < N_V4 && y0 + r < H)
-          held[i] = __ldg(reinterpret_cast<const float4 *>(block_grad + (r * W * A + 4 * c)));
+      const int n_rows = min(4, H - y0);
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(&grad_ready[warp]);
+      if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(n_rows * 32 * A)) : "memory");
+        for (int r = 0; r < n_rows; ++r) {
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + r * 8 * A);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst), "l"(block_grad + (size_t)r * W * A), "r"((unsigned)(32 * A)), "r"(bar) : "memory");
+        }
       }
       if (id >= 0) {
         const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
         pv0 = __ldg(v4 + vid[0]); pv1 = __ldg(v4 + vid[1]); pv2 = __ldg(v4 + vid[2]);
       }
-#pragma unroll
-      for (int i = 0; i < PER_LANE; ++i) {
-        const int k = lane + 32 * i;
-        const int r = k / V4_PER_ROW;
-        if (k < N_V4 && y0 + r < H) reinterpret_cast<float4 *>(stage)[k] = held[i];     // rows back to back
+      __syncwarp();                               // the barrier is initialised before anyone polls it
+      unsigned done = 0;
+      while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar) : "memory");
       }
-      __syncwarp();
 #pragma unroll
       for (int a = 0; a < A; ++a) g_local[a] = stage[lane * A + a];
       __syncwarp();                               // staging consumed; the area becomes the rows
