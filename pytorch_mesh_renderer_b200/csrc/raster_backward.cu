@@ -176,6 +176,12 @@ backward_atomic_kernel(const float *__restrict__ grad, const float *__restrict__
   }
 }
 
+// Predicated fire-and-forget float add (RED): lanes without a destination skip it without a branch.
+__device__ __forceinline__ void red_add_if(bool ok, float *addr, float v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\t@p red.global.add.f32 [%1], %2;\n\t}"
+               ::"r"((int)ok), "l"(addr), "f"(v) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Atomic mode, warp-aggregated: the throughput path
 // ---------------------------------------------------------------------------------------------
@@ -194,23 +200,21 @@ __global__ void __launch_bounds__(kBlockWarps * 32, (kBlockWarps == 8 ? 5 : 8))
 backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__ verts,
                        const float *__restrict__ attrs, const int32_t *__restrict__ tris,
                        const int32_t *__restrict__ ids, const float *__restrict__ bary,
-                       int V, int W, int H, int blocks_x, int blocks_per_image,
-                       float *__restrict__ d_verts, float *__restrict__ d_attrs) {
+                       int V, int W, int H, float *__restrict__ d_verts, float *__restrict__ d_attrs) {
   constexpr int A = A_STATIC;
   constexpr int NV = 9 + (FUSED ? 3 * A : 0);
   constexpr int STRIDE = (NV + 3) | 1;           // NV sums + 3 vertex ids, odd => conflict-free rows
   // per warp: 32 rows of NV sums + 3 vertex ids; the gradient staging area aliases the rows (it is
   // consumed into registers before the first row is written)
-  __shared__ __align__(16) float rows_all[kBlockWarps][32 * STRIDE + 4];
+  __shared__ __align__(16) float rows_all[kBlockWarps][32 * STRIDE + 36];   // + padding read by column-less lanes
   __shared__ __align__(8) unsigned long long grad_ready[kBlockWarps];      // mbarriers of the bulk gradient loads
   static_assert(32 * STRIDE >= 32 * A, "gradient staging must fit the row area");
 
+  // The CTA covers 2 x (kBlockWarps/2) pixel blocks: 16 pixels wide, 2*kBlockWarps rows high.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rem = blockIdx.x * kBlockWarps + warp;        // 8x4 block within the image
-  if (rem >= blocks_per_image) return;
-  const int b = blockIdx.y;
-  const int by = rem / blocks_x;
-  const int x0 = (rem - by * blocks_x) * 8, y0 = by * 4;
+  const int b = blockIdx.z;
+  const int x0 = (blockIdx.x * 2 + (warp & 1)) * 8, y0 = (blockIdx.y * (kBlockWarps / 2) + (warp >> 1)) * 4;
+  if (x0 >= W || y0 >= H) return;
   const int ix = x0 + (lane & 7), iy = y0 + (lane >> 3);
   const bool in_image = ix < W && iy < H;
   const long long p = ((long long)b * H + iy) * W + ix;
@@ -290,10 +294,22 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
     }
   }
 
+  // Group the covered lanes by triangle and give every covered lane a ROW: the rows of one triangle
+  // are consecutive (groups ordered by their first lane), so the reduction below is a linear walk.
+  // Uncovered lanes get private keys, match nobody and own no row.
+  const unsigned peers = __match_any_sync(0xffffffffu, id >= 0 ? id : -1 - lane);
+  const int leader = __ffs(peers) - 1;
+  const int group_size = __popc(peers), rank = __popc(peers & ((1u << lane) - 1u));
+  const int lead_size = (id >= 0 && lane == leader) ? group_size : 0;
+  const int before = warp_inclusive_scan(lead_size) - lead_size;        // rows of the groups led by lower lanes
+  const int pos = __shfl_sync(0xffffffffu, before, leader) + rank;
+  // bit r set: row r is the last row of its group
+  unsigned ends = __reduce_or_sync(0xffffffffu, (id >= 0 && rank == group_size - 1) ? (1u << pos) : 0u);
+
   if (id >= 0) {
     PixelGrad pg;
     pixel_grad_loaded<FUSED>(vid, pv0, pv1, pv2, attrs_b, bp, g_local, A, pg);
-    float *row = rows + lane * STRIDE;
+    float *row = rows + pos * STRIDE;
 #pragma unroll
     for (int k = 0; k < 9; ++k) row[k] = pg.terms[k];
     if (FUSED) {
@@ -305,52 +321,54 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
 #pragma unroll
     for (int j = 0; j < 3; ++j) row[NV + j] = __int_as_float(pg.vid[j]);
   }
-  // Group the covered lanes by triangle.  Uncovered lanes get private keys so they match nobody.
-  const unsigned peers = __match_any_sync(0xffffffffu, id >= 0 ? id : -1 - lane);
-  const bool is_leader = id >= 0 && (__ffs(peers) - 1) == lane;
-  unsigned leaders = __ballot_sync(0xffffffffu, is_leader);
   __syncwarp();
 
-  // Lane c owns column c (and column c + 32 when NV > 32) of every group.  The walk over groups
-  // and over the lanes of a group is warp-uniform, so only the shared-memory read and the add are
-  // per-lane work.  Column -> (corner, offset in the vertex row) depends on the lane only.
+  // Lane c owns column c (and column c + 32 when NV > 32) of every group: it adds its column over the
+  // group's rows and issues ONE atomic per (group, column).  Column -> (corner, destination) depends
+  // on the lane only: columns 0..8 are the vertex terms [3*corner + {x,y,w}] -> d_verts[vtx*4 + {0,1,3}],
+  // columns 9.. are [corner][attribute] -> d_attrs[vtx*A + attribute].  All lanes issue the same
+  // instruction; consecutive lanes hit consecutive words of a vertex row.
   const int c0 = lane, c1 = lane + 32;
-  const bool has0 = c0 < NV, has1 = c1 < NV;
-  auto corner_of = [](int c) { return c < 9 ? c / 3 : (c - 9) / (A > 0 ? A : 1); };
-  auto offset_of = [](int c) { return c < 9 ? column_of(c % 3) : (c - 9) % (A > 0 ? A : 1); };
-  const int corner0 = has0 ? corner_of(c0) : 0, corner1 = has1 ? corner_of(c1) : 0;
-  const int off0 = has0 ? offset_of(c0) : 0, off1 = has1 ? offset_of(c1) : 0;
+  const int corner0 = c0 < 9 ? c0 / 3 : (c0 - 9) / (A > 0 ? A : 1);
+  const int corner1 = (c1 - 9) / (A > 0 ? A : 1);
   float *dv = d_verts ? d_verts + (size_t)b * V * 4 : nullptr;
   float *da = (FUSED && d_attrs) ? d_attrs + (size_t)b * V * A : nullptr;
-  while (leaders) {
-    const int leader = __ffs(leaders) - 1;
-    leaders &= leaders - 1;
-    unsigned members = __shfl_sync(0xffffffffu, peers, leader);
+  float *dst0 = c0 < 9 ? (dv ? dv + column_of(c0 % 3) : nullptr) : (da ? da + (c0 - 9) % (A > 0 ? A : 1) : nullptr);
+  float *dst1 = da ? da + (c1 - 9) % (A > 0 ? A : 1) : nullptr;
+  const int pitch0 = c0 < 9 ? 4 : A;
+  if (c0 >= NV) dst0 = nullptr;
+  if (c1 >= NV) dst1 = nullptr;
+  // Lanes without a column read column 0 / a neighbouring row's words (the row area is padded) and
+  // drop the sum, so that the row loads are unpredicated.
+  const float *col = rows + (c0 < NV ? c0 : 0);
+  const int *vtx0_at = reinterpret_cast<const int *>(rows) + NV + corner0;
+  const int *vtx1_at = reinterpret_cast<const int *>(rows) + NV + (c1 < NV ? corner1 : 0);
+  int r = 0;
+  while (ends) {
+    const int last = __ffs(ends) - 1;                   // rows r..last form one group (warp-uniform)
+    ends &= ends - 1;
+    const float *q = col + r * STRIDE;
+    int n = last - r + 1;
     float acc0 = 0.0f, acc1 = 0.0f;
-    while (members) {                                   // two members per trip
-      const int src = __ffs(members) - 1;
-      members &= members - 1;
-      const float *row = rows + src * STRIDE;
-      if (has0) acc0 += row[c0];
-      if (NV > 32 && has1) acc1 += row[c1];
-      if (members) {
-        const int src2 = __ffs(members) - 1;
-        members &= members - 1;
-        const float *row2 = rows + src2 * STRIDE;
-        if (has0) acc0 += row2[c0];
-        if (NV > 32 && has1) acc1 += row2[c1];
-      }
+    for (; n > 8; --n, q += STRIDE) {                    // rare: more than 8 pixels of one triangle
+      acc0 += q[0];
+      if (NV > 32) acc1 += q[32];
     }
-    const float *lrow = rows + leader * STRIDE;
-    if (has0) {
-      const size_t vtx = (size_t)__float_as_int(lrow[NV + corner0]);
-      if (c0 < 9) { if (dv) atomicAdd(dv + vtx * 4 + off0, acc0); }
-      else if (da) atomicAdd(da + vtx * A + off0, acc0);
+#define PMR_ROW(k) acc0 += q[(k) * STRIDE]; if (NV > 32) acc1 += q[(k) * STRIDE + 32];
+    switch (n) {                                        // straight-line code per group size
+      case 8: PMR_ROW(7)
+      case 7: PMR_ROW(6)
+      case 6: PMR_ROW(5)
+      case 5: PMR_ROW(4)
+      case 4: PMR_ROW(3)
+      case 3: PMR_ROW(2)
+      case 2: PMR_ROW(1)
+      default: PMR_ROW(0)
     }
-    if (NV > 32 && has1) {
-      const size_t vtx = (size_t)__float_as_int(lrow[NV + corner1]);
-      if (da) atomicAdd(da + vtx * A + off1, acc1);
-    }
+#undef PMR_ROW
+    r = last + 1;
+    red_add_if(dst0 != nullptr, dst0 + (unsigned)(vtx0_at[last * STRIDE] * pitch0), acc0);
+    if (NV > 32) red_add_if(dst1 != nullptr, dst1 + (unsigned)(vtx1_at[last * STRIDE] * A), acc1);
   }
 }
 
@@ -500,11 +518,10 @@ int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, 
     if (d_verts) PMR_CUDA(ctx, cudaMemsetAsync(d_verts, 0, (size_t)n_pairs * 4 * sizeof(float), stream));
     if (fused && d_attrs) PMR_CUDA(ctx, cudaMemsetAsync(d_attrs, 0, (size_t)n_pairs * A * sizeof(float), stream));
     if (total == 0 || T == 0) return PMR_OK;
-    const int blocks_x = (W + 7) / 8, blocks_y = (H + 3) / 4;
-    const int blocks_per_image = blocks_x * blocks_y;
+    if (B > 65535) return set_error(ctx, PMR_ERR_SIZE, "batch exceeds 65535 images");
 #define PMR_BLOCKS(F, AS, WARPS)                                                                          \
-  backward_blocks_kernel<F, AS, WARPS><<<dim3((blocks_per_image + WARPS - 1) / WARPS, B), WARPS * 32, 0, stream>>>(  \
-      grad, verts, attrs, tris, ids, bary, V, W, H, blocks_x, blocks_per_image, d_verts, d_attrs)
+  backward_blocks_kernel<F, AS, WARPS><<<dim3((W + 15) / 16, (H + 2 * WARPS - 1) / (2 * WARPS), B), WARPS * 32, 0, stream>>>(  \
+      grad, verts, attrs, tris, ids, bary, V, W, H, d_verts, d_attrs)
     if (!fused) PMR_BLOCKS(false, 1, 8);
     else if (A == 9) PMR_BLOCKS(true, 9, 8);
     else if (A == 4) PMR_BLOCKS(true, 4, 8);
