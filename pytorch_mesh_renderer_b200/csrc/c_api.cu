@@ -86,6 +86,7 @@ static int validate_common(Context *ctx, int B, int V, int T, int W, int H) {
   if (W <= 0) return set_error(ctx, PMR_ERR_INVALID, "Image width must be > 0.");
   if (H <= 0) return set_error(ctx, PMR_ERR_INVALID, "Image height must be > 0.");
   if (W > 32768 || H > 32768) return set_error(ctx, PMR_ERR_SIZE, "image larger than 32768 pixels on a side");
+  if (B > 65535) return set_error(ctx, PMR_ERR_SIZE, "more than 65535 images per call (the image index is a grid dimension)");
   PMR_CUDA(ctx, cudaSetDevice(ctx->device));
   return PMR_OK;
 }

@@ -350,6 +350,7 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
     const float *q = col + r * STRIDE;
     int n = last - r + 1;
     float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 1
     for (; n > 8; --n, q += STRIDE) {                    // rare: more than 8 pixels of one triangle
       acc0 += q[0];
       if (NV > 32) acc1 += q[32];
@@ -518,7 +519,6 @@ int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, 
     if (d_verts) PMR_CUDA(ctx, cudaMemsetAsync(d_verts, 0, (size_t)n_pairs * 4 * sizeof(float), stream));
     if (fused && d_attrs) PMR_CUDA(ctx, cudaMemsetAsync(d_attrs, 0, (size_t)n_pairs * A * sizeof(float), stream));
     if (total == 0 || T == 0) return PMR_OK;
-    if (B > 65535) return set_error(ctx, PMR_ERR_SIZE, "batch exceeds 65535 images");
 #define PMR_BLOCKS(F, AS, WARPS)                                                                          \
   backward_blocks_kernel<F, AS, WARPS><<<dim3((W + 15) / 16, (H + 2 * WARPS - 1) / (2 * WARPS), B), WARPS * 32, 0, stream>>>(  \
       grad, verts, attrs, tris, ids, bary, V, W, H, d_verts, d_attrs)

@@ -200,8 +200,7 @@ __device__ __forceinline__ void evaluate_winner(const float4 &p0, const float4 &
 // multiple of 16) handed to the bulk-copy engine: cp.async.bulk shared::cta -> global (SASS UBLKCP).
 // The issuing lane commits the group and must wait for the reads (bulk_store_wait) before the
 // shared memory is reused or the CTA exits.
-__device__ __forceinline__ void bulk_store_row(float *dst, const float *src_shared, unsigned bytes) {
-  const unsigned src = (unsigned)__cvta_generic_to_shared(src_shared);
+__device__ __forceinline__ void bulk_store_row(float *dst, unsigned src, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
@@ -282,11 +281,17 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy reads
     __syncwarp();
     if (lane == 0) {
+      float *bary_row = out_bary + 3 * p0, *image_row = out_image != nullptr ? out_image + p0 * A : nullptr;
+      const unsigned stage_at = (unsigned)__cvta_generic_to_shared(stage);
+      const int bary_pitch = 3 * W, image_pitch = W * A;                // floats per image row
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        bulk_store_row(out_bary + 3 * (p0 + (size_t)r * W), stage + r * 24, 96u);
-        if (out_image != nullptr)
-          bulk_store_row(out_image + (p0 + (size_t)r * W) * A, stage + kImageAt + r * 8 * A, 32u * (unsigned)A);
+        bulk_store_row(bary_row, stage_at + r * 96, 96u);
+        bary_row += bary_pitch;
+        if (out_image != nullptr) {
+          bulk_store_row(image_row, stage_at + 4 * (kImageAt + r * 8 * A), 32u * (unsigned)A);
+          image_row += image_pitch;
+        }
       }
       bulk_store_commit_and_wait();
     }
@@ -716,7 +721,7 @@ constexpr int kResolveWarps = 8;
 template <int A_STATIC>
 __global__ void __launch_bounds__(kResolveWarps * 32)
 resolve_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int W, int H,
-               int blocks_x, int blocks_per_image, const float *__restrict__ centers,
+               const float *__restrict__ centers,
                const unsigned long long *__restrict__ keys,
                int32_t *__restrict__ out_ids, float *__restrict__ out_bary, float *__restrict__ out_z,
                const float *__restrict__ attrs, const float *__restrict__ background, int A_dyn,
@@ -724,11 +729,10 @@ resolve_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris
   __shared__ __align__(16) float stage_all[kResolveWarps][32 * 16];
   const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rem = blockIdx.x * kResolveWarps + warp;
-  if (rem >= blocks_per_image) return;
-  const int b = blockIdx.y;
-  const int by = rem / blocks_x;
-  const int blk_x0 = (rem - by * blocks_x) * 8, blk_y0 = by * 4;
+  // the CTA covers a 16x16 pixel tile: 2 blocks across, 4 down
+  const int b = blockIdx.z;
+  const int blk_x0 = (blockIdx.x * 2 + (warp & 1)) * 8, blk_y0 = (blockIdx.y * (kResolveWarps / 2) + (warp >> 1)) * 4;
+  if (blk_x0 >= W || blk_y0 >= H) return;
   const int ix = blk_x0 + (lane & 7), iy = blk_y0 + (lane >> 3);
   Fragment best;
   fragment_clear(best);
@@ -881,10 +885,9 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
   }
   {
     StageScope timed(ctx, PMR_STAGE_RESOLVE, stream);
-    const int blocks_x = (W + 7) / 8, blocks_y = (H + 3) / 4, bpi = blocks_x * blocks_y;
-    dim3 grid((bpi + kResolveWarps - 1) / kResolveWarps, B);
+    dim3 grid((W + 15) / 16, (H + 2 * kResolveWarps - 1) / (2 * kResolveWarps), B);
 #define PMR_RESOLVE(AS)                                                                                          \
-  resolve_kernel<AS><<<grid, kResolveWarps * 32, 0, stream>>>(verts, tris, V, W, H, blocks_x, bpi, centers, keys, ids, \
+  resolve_kernel<AS><<<grid, kResolveWarps * 32, 0, stream>>>(verts, tris, V, W, H, centers, keys, ids,          \
                                                               bary, z, attrs, bg, A, image)
     if (image == nullptr) PMR_RESOLVE(0);
     else if (A == 4) PMR_RESOLVE(4);
