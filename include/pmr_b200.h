@@ -25,8 +25,9 @@
  *   - `vertices` must be 16-byte aligned.  Vertex indices are not range-checked (neither does the
  *     reference, K.cpp:331-337).
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Kernels are
- *     enqueued on it; only the forward pass of a binned mesh synchronises it once (8-byte
- *     read-back of the tile-list length).  A context must not be used from two streams at once.
+ *     enqueued on it and nothing on the device-pointer entry points waits for the device (the
+ *     passes are capturable in a CUDA graph once the workspace has grown to size).  A context
+ *     must not be used from two streams at once.
  *   - Every function returns PMR_OK (0) or a negative PMR_ERR_* code; pmr_last_error() gives the
  *     message.  There is no CPU fallback: without a CUDA device pmr_create fails.
  *   - Outputs are fully written by the callee (no pre-initialisation required).
@@ -62,16 +63,17 @@ typedef struct pmr_context pmr_context;
 
 PMR_API int pmr_version(void);
 
-/* Creates a context (workspace + pinned mailbox) on CUDA device `device`. */
+/* Creates a context (grow-only device workspace) on CUDA device `device`. */
 PMR_API int pmr_create(int device, pmr_context **out);
 PMR_API void pmr_destroy(pmr_context *ctx);
 PMR_API const char *pmr_last_error(const pmr_context *ctx);
 
 /* Number of kernels launched through this context so far (bench.py's gpu_launches). */
 PMR_API long long pmr_launch_count(const pmr_context *ctx);
-/* Tile-list entries produced by the last binned forward pass (diagnostics). */
-PMR_API unsigned long long pmr_last_bin_entries(const pmr_context *ctx);
-/* Meshes with at most this many triangles skip the binning pass (default 64). */
+/* Triangles whose pixel box exceeded 16x16 in the last pipeline forward pass, summed over its images
+ * (the ones raster_tile_kernel drew).  Diagnostics: synchronises the device. */
+PMR_API long long pmr_last_large_triangles(pmr_context *ctx);
+/* Meshes with at most this many triangles (default 64, effective maximum 1024) run the tile kernel alone. */
 PMR_API int pmr_set_small_mesh_threshold(pmr_context *ctx, int triangles);
 
 /*
@@ -82,11 +84,11 @@ PMR_API int pmr_set_small_mesh_threshold(pmr_context *ctx, int triangles);
  * running totals held by the context, copies the totals out and, if `reset` is non-zero,
  * clears them.
  */
-#define PMR_STAGE_BIN 0      /* key clear + bin_offsets + length read-back + bin_fill */
+#define PMR_STAGE_BIN 0      /* clearing the depth keys and the large-triangle counters */
 #define PMR_STAGE_RASTER 1   /* raster_tile_kernel (big triangles; whole pass for tiny meshes) */
 #define PMR_STAGE_BACKWARD 2 /* backward kernels (atomic: one kernel; ordered: boxes + gather) */
 #define PMR_STAGE_INTERP 3   /* standalone interpolate_kernel */
-#define PMR_STAGE_SCATTER 4  /* scatter_small_kernel (small triangles -> depth keys; bins the big ones) */
+#define PMR_STAGE_SCATTER 4  /* scatter_small_kernel (small triangles -> depth keys; lists the large ones) */
 #define PMR_STAGE_RESOLVE 5  /* resolve_kernel (depth keys -> ids / bary / z / interpolated image) */
 #define PMR_STAGE_COUNT 6
 PMR_API int pmr_enable_stage_timing(pmr_context *ctx, int enable);

@@ -29,7 +29,7 @@ _PROTOTYPES = {
     "pmr_destroy": (None, [_vp]),
     "pmr_last_error": (ctypes.c_char_p, [_vp]),
     "pmr_launch_count": (ctypes.c_longlong, [_vp]),
-    "pmr_last_bin_entries": (ctypes.c_ulonglong, [_vp]),
+    "pmr_last_large_triangles": (ctypes.c_longlong, [_vp]),
     "pmr_set_small_mesh_threshold": (ctypes.c_int, [_vp, _i]),
     "pmr_enable_stage_timing": (ctypes.c_int, [_vp, _i]),
     "pmr_read_stage_timing": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), _i]),

@@ -115,10 +115,6 @@ int pmr_create(int device, pmr_context **out) {
   if (!ctx) return PMR_ERR_INVALID;
   ctx->device = device;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (cudaMallocHost((void **)&ctx->mailbox, 64) != cudaSuccess) {
-    delete ctx;
-    return PMR_ERR_CUDA;
-  }
   *out = ctx;
   return PMR_OK;
 }
@@ -127,11 +123,9 @@ void pmr_destroy(pmr_context *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   ctx->bins.release();
-  ctx->lists.release();
   ctx->scratch.release();
   ctx->keys.release();
   ctx->centers.release();
-  if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   if (ctx->call_begin) cudaEventDestroy(ctx->call_begin);
@@ -142,7 +136,18 @@ void pmr_destroy(pmr_context *ctx) {
 
 const char *pmr_last_error(const pmr_context *ctx) { return ctx ? ctx->error : "null context"; }
 long long pmr_launch_count(const pmr_context *ctx) { return ctx ? ctx->launches : 0; }
-unsigned long long pmr_last_bin_entries(const pmr_context *ctx) { return ctx ? ctx->last_bin_entries : 0; }
+long long pmr_last_large_triangles(pmr_context *ctx) {
+  // Diagnostics only: blocking copy of the per-image counters the last pipeline forward left on the device.
+  if (!ctx) return PMR_ERR_INVALID;
+  if (ctx->last_large_count == nullptr || ctx->last_large_images <= 0) return 0;
+  std::vector<int> counts((size_t)ctx->last_large_images);
+  if (cudaSetDevice(ctx->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(counts.data(), ctx->last_large_count, counts.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return set_error(ctx, PMR_ERR_CUDA, "reading the large-triangle counters failed: %s", cudaGetErrorString(cudaGetLastError()));
+  long long total = 0;
+  for (int c : counts) total += c;
+  return total;
+}
 
 int pmr_enable_stage_timing(pmr_context *ctx, int enable) {
   if (!ctx) return PMR_ERR_INVALID;

@@ -36,12 +36,12 @@ struct Context {
   int device = 0;
   int sm_count = 148;
   int small_mesh_threshold = 64;      // T at or below this: no binning, every tile walks all triangles
-  Buffer bins, lists, scratch, keys, centers;
+  Buffer bins, scratch, keys, centers;
   int centers_w = -1, centers_h = -1;  // image size the pixel-centre table was built for
-  unsigned long long *mailbox = nullptr;   // pinned host word for the tile-list length
   cudaStream_t copy_stream = nullptr;       // host entry point: uploads the image gradient while the forward runs
   cudaEvent_t copy_done = nullptr, call_begin = nullptr;
-  unsigned long long last_bin_entries = 0;
+  const int *last_large_count = nullptr;    // device: large triangles per image of the last pipeline forward
+  int last_large_images = 0;
   long long launches = 0;             // kernels launched through this context (bench gpu_launches)
   char error[512] = {0};
   // stage timing (pmr_enable_stage_timing)

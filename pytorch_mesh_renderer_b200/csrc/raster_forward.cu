@@ -10,14 +10,15 @@
 //                         inside pixels are compacted and dealt to the lanes again for barycentrics /
 //                         depth, and each one does atomicMin on the pixel's key in global memory (L2).
 //                         No per-tile duplication of triangle setup, no binning for these triangles.
-//                         Larger triangles are only counted into the 16x16 screen tiles they touch.
-//   bin_offsets_kernel    warp-aggregated allocation of one contiguous list range per tile
-//   bin_fill_kernel       writes the ids of the LARGE triangles into the tile lists
-//   raster_tile_kernel    one CTA per tile for the large triangles: setup records staged in shared
-//                         memory, a warp per 8x4 pixel block culls them with a ballot, one lane per
-//                         pixel keeps its winner in registers (parts of large triangles that are small
-//                         inside the tile take the segment path on a shared-memory key), result merged
-//                         into the global keys.  Skipped when no triangle is large.
+//                         Larger triangles are appended (id + pixel box) to the image's LARGE list.
+//   raster_tile_kernel    persistent CTAs walk the 16x16 screen tiles of the images that have large
+//                         triangles: the image's large list is scanned with a box-vs-tile test, the
+//                         survivors are staged 256 at a time as setup records in shared memory, a warp
+//                         per 8x4 pixel block culls them with a ballot, one lane per pixel keeps its
+//                         winner in registers (parts of large triangles that are small inside the tile
+//                         take the segment path on a shared-memory key), result merged into the global
+//                         keys.  Images without large triangles cost one load per tile; the whole
+//                         pass needs no host round trip (no list sizes to read back).
 //   resolve_kernel        one warp per 8x4 pixel block: decodes the winner, re-evaluates its
 //                         barycentrics / depth once (same arithmetic, same bits), interpolates the
 //                         attributes and stores ids / z / barycentrics / image as 16-byte vectors
@@ -46,74 +47,6 @@ __device__ __forceinline__ int4 unpack_box(uint2 p) {
   return make_int4((int)(p.x & 0xffffu), (int)(p.x >> 16), (int)(p.y & 0xffffu), (int)(p.y >> 16));
 }
 
-// Visits every tile touched by the boxes held by the lanes of a warp.  Ranges of up to
-// kSerialTiles tiles are walked by their own lane; larger ones are walked by the whole warp
-// so that one screen-filling triangle does not serialise 16k atomics on a single thread.
-template <typename Visit>
-__device__ __forceinline__ void for_each_tile(uint2 packed, int tiles_x, Visit visit) {
-  const int4 box = unpack_box(packed);
-  const bool empty = box.x >= box.y || box.z >= box.w;
-  const int tx0 = box.x >> kTileShiftX, tx1 = empty ? tx0 : (box.y + kTileW - 1) >> kTileShiftX;
-  const int ty0 = box.z >> kTileShiftY, ty1 = empty ? ty0 : (box.w + kTileH - 1) >> kTileShiftY;
-  const int nx = tx1 - tx0, n = nx * (ty1 - ty0);
-  constexpr int kSerialTiles = 8;
-  if (n > 0 && n <= kSerialTiles) {
-    for (int ty = ty0; ty < ty1; ++ty)
-      for (int tx = tx0; tx < tx1; ++tx) visit(ty * tiles_x + tx, /*owner_lane=*/-1);
-  }
-  unsigned big = __ballot_sync(0xffffffffu, n > kSerialTiles);
-  const int lane = threadIdx.x & 31;
-  while (big) {
-    const int src = __ffs(big) - 1;
-    big &= big - 1;
-    const int sx0 = __shfl_sync(0xffffffffu, tx0, src), snx = __shfl_sync(0xffffffffu, nx, src);
-    const int sy0 = __shfl_sync(0xffffffffu, ty0, src), sn = __shfl_sync(0xffffffffu, n, src);
-    for (int k = lane; k < sn; k += 32) {
-      const int ty = sy0 + k / snx, tx = sx0 + k % snx;
-      visit(ty * tiles_x + tx, src);
-    }
-  }
-}
-
-// One contiguous range per tile; ranges are handed out warp by warp from a global cursor, so
-// their order in the list buffer is arbitrary (nothing depends on it).
-__global__ void __launch_bounds__(256)
-bin_offsets_kernel(const int *__restrict__ tile_counts, int n_tiles, int *__restrict__ tile_offsets,
-                   unsigned long long *__restrict__ total) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const int c = i < n_tiles ? tile_counts[i] : 0;
-  int incl = c;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int up = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += up;
-  }
-  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-  unsigned long long base = 0;
-  if (lane == 31 && warp_total > 0) base = atomicAdd(total, (unsigned long long)warp_total);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  // Offsets beyond 2^31 entries are refused on the host before the fill kernel runs.
-  if (i < n_tiles) tile_offsets[i] = (int)(base + (unsigned long long)(incl - c));
-}
-
-__global__ void __launch_bounds__(256)
-bin_fill_kernel(const uint2 *__restrict__ tri_boxes, int T, int tiles_x, int tiles_per_image,
-                const int *__restrict__ tile_offsets, int *__restrict__ tile_cursors,
-                int32_t *__restrict__ tile_lists) {
-  const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint2 packed = t < T ? tri_boxes[(size_t)b * T + t] : make_uint2(0u, 0u);
-  const int *offsets = tile_offsets + (size_t)b * tiles_per_image;
-  int *cursors = tile_cursors + (size_t)b * tiles_per_image;
-  const int lane = threadIdx.x & 31;
-  for_each_tile(packed, tiles_x, [&](int tile, int owner) {
-    const int tri = owner < 0 ? t : (t - lane + owner);
-    const int slot = atomicAdd(cursors + tile, 1);
-    tile_lists[(size_t)offsets[tile] + slot] = tri;
-  });
-}
-
 // ---------------------------------------------------------------------------------------------
 // Per-tile raster kernel
 // ---------------------------------------------------------------------------------------------
@@ -122,6 +55,8 @@ constexpr int kChunk = 256;                 // triangles staged per round == thr
 constexpr int kTilePixels = kTileW * kTileH;
 constexpr int kWarps = kChunk / 32;
 constexpr int kWarpSegCap = 256;            // row segments of small triangles a warp holds per round
+
+constexpr int kMacroCapacity = 1024;        // see kMacroCap below
 
 struct TileSmem {
   // Setup record of one staged triangle, split into float4 planes so that staging stores are
@@ -138,7 +73,12 @@ struct TileSmem {
   unsigned short big_list[kChunk];
   int depth_bucket[32], depth_cursor[32];   // front-to-back ordering of the big list (32 depth slices)
   float cx[kTileW], cy[kTileH];          // pixel-centre NDC coordinates of the tile's columns / rows
-  int n_big;
+  unsigned short cand[2 * kChunk];       // macro-list entries that passed the box-vs-tile test
+  uint2 mbox[kMacroCapacity];            // macro list: packed pixel boxes ...
+  int mslot[kMacroCapacity];             // ... and positions in the image's candidate list
+  unsigned short active[kChunk];         // images of the current slice that have candidates (B <= 65535)
+  int warp_count[kWarps];
+  int n_big, n_cand, n_macro, next_item;
 };
 
 // After the raster loop the record planes are dead; the epilogue reuses them to transpose each warp's
@@ -302,262 +242,379 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
     store_block_rows<(A_STATIC > 0 ? A_STATIC : 1)>(stage + kImageAt, out_image + p0 * A, W * A, cols, rows, vec_ok);
 }
 
+// Packed pixel box vs the pixel rectangle [x0, x0 + w) x [y0, y0 + h).
+__device__ __forceinline__ bool box_touches_rect(uint2 packed, int x0, int y0, int w, int h) {
+  const int4 bx = unpack_box(packed);
+  return bx.x < x0 + w && bx.y > x0 && bx.z < y0 + h && bx.w > y0;
+}
+
+constexpr int kMacroTiles = 4;               // a macro tile is up to 4 x 4 screen tiles = 64 x 64 pixels
+constexpr int kMacroCap = kMacroCapacity;    // candidates a macro tile holds per pass
+constexpr int kScanRound = 2 * kChunk;       // candidates examined per scan round (two per thread)
+constexpr int kTinyMeshMax = kMacroCap;      // largest mesh the tiny-mesh mode accepts
+
+// Persistent kernel.  Work items are (image, macro tile) pairs of the images that have candidates; CTA i
+// takes items i, i + gridDim.x, ...  Per item the image's candidate list is scanned ONCE against the
+// macro tile (64x64 pixels) into shared memory; each of its 16 screen tiles then filters that short
+// list against its own rectangle, stages the survivors 256 at a time and rasterizes them.  Nothing here
+// needs list sizes on the host: memory is bounded by the per-image list (T entries) and, when a macro
+// tile has more than kMacroCap candidates, the item is done in several passes that merge through the
+// global depth keys.
+//   large_count == nullptr   tiny-mesh mode (T <= kTinyMeshMax): every tile walks all T triangles, boxes
+//                            are computed here and the tile writes ids / barycentrics / z / image itself
+//                            (keys_out == nullptr);
+//   large_count != nullptr   pipeline mode: image b has large_count[b] large triangles, ids and packed
+//                            boxes in large_ids / large_boxes[b * T ...]; the result is merged into keys_out.
 template <int A_STATIC>
-__global__ void __launch_bounds__(kChunk, 5)
+__global__ void __launch_bounds__(kChunk, 4)
 raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris,
-                   int V, int T, int W, int H, float half_w, float half_h, int tiles_per_image,
-                   const int *__restrict__ tile_counts, const int *__restrict__ tile_offsets,
-                   const int32_t *__restrict__ tile_lists, const uint2 *__restrict__ tri_boxes,
+                   int B, int V, int T, int W, int H, float half_w, float half_h, int tiles_x, int tiles_y,
+                   int macro_tiles, int *__restrict__ work_cursor, const int *__restrict__ large_count, const int32_t *__restrict__ large_ids,
+                   const uint2 *__restrict__ large_boxes,
                    int32_t *__restrict__ out_ids, float *__restrict__ out_bary, float *__restrict__ out_z,
                    const float *__restrict__ attrs, const float *__restrict__ background, int A_dyn,
                    float *__restrict__ out_image, unsigned long long *__restrict__ keys_out) {
   __shared__ __align__(16) TileSmem sm;
   const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
-  const int b = blockIdx.z;
-  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  const int tile_x0 = blockIdx.x * kTileW, tile_y0 = blockIdx.y * kTileH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lanes_below = (1u << lane) - 1u;
+  const int macros_x = (tiles_x + macro_tiles - 1) / macro_tiles, macros_y = (tiles_y + macro_tiles - 1) / macro_tiles;
+  const int macros_per_image = macros_x * macros_y;
+  // Work items are handed out through a global counter (item costs differ by an order of magnitude
+  // between busy and empty screen regions); `grabbed` only ever grows, the slices consume it in order.
+  auto grab_item = [&]() {
+    __syncthreads();
+    if (threadIdx.x == 0) sm.next_item = atomicAdd(work_cursor, 1);
+    __syncthreads();
+    return sm.next_item;
+  };
+  int grabbed = grab_item();
+  int slice_begin = 0;
+  const bool pipeline = large_count != nullptr;
   // 8 warps, each an 8x4 pixel block; blocks are laid out 2 across, 4 down inside the 16x16 tile.
   const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
-  const int blk_x0 = tile_x0 + (warp & 1) * 8, blk_y0 = tile_y0 + (warp >> 1) * 4;
-  const int ix = tile_x0 + lx, iy = tile_y0 + ly;
-  const float *verts_b = verts + (size_t)b * V * 4;
 
-  sm.key[threadIdx.x] = kEmptyKey;
-  if (threadIdx.x < kTileW) sm.cx[threadIdx.x] = pixel_center(tile_x0 + threadIdx.x, half_w);
-  else if (threadIdx.x < kTileW + kTileH) sm.cy[threadIdx.x - kTileW] = pixel_center(tile_y0 + threadIdx.x - kTileW, half_h);
-  if (threadIdx.x == 0) sm.n_big = 0;
-  if (threadIdx.x < 32) { sm.depth_bucket[threadIdx.x] = 0; sm.depth_cursor[threadIdx.x] = 0; }
-
-  int n_list;
-  const int32_t *list = nullptr;
-  if (tile_lists != nullptr) {
-    const size_t g = (size_t)b * tiles_per_image + tile;
-    n_list = tile_counts[g];
-    list = tile_lists + tile_offsets[g];
-  } else {
-    n_list = T;            // small mesh: every tile walks all triangles
-  }
-
-  Fragment best;
-  fragment_clear(best);
-  __syncthreads();         // publishes key / cx / cy / n_big
-  const float px = sm.cx[lx], py = sm.cy[ly];
-  // pixel-centre range of this warp's 8x4 block (for the conservative edge test of the big path)
-  const float blk_px0 = sm.cx[(warp & 1) * 8], blk_px1 = sm.cx[(warp & 1) * 8 + 7];
-  const float blk_py0 = sm.cy[(warp >> 1) * 4], blk_py1 = sm.cy[(warp >> 1) * 4 + 3];
-  const float blk_pxabs = fmaxf(fabsf(blk_px0), fabsf(blk_px1)), blk_pyabs = fmaxf(fabsf(blk_py0), fabsf(blk_py1));
-  if (keys_out != nullptr && ix < W && iy < H) {
-    // binned pipeline: start from what the small triangles already drew (depth and id are all the
-    // depth rule needs; barycentrics are not produced in this mode)
-    const unsigned long long seen = keys_out[((size_t)b * H + iy) * W + ix];
-    if (seen != kEmptyKey) { best.z = ordered_to_float((unsigned)(seen >> 32)); best.id = depth_key_id(seen); }
-  }
-
-  for (int base = 0; base < n_list; base += kChunk) {
-    const int n_here = min(kChunk, n_list - base);
-    if (base > 0) {
-      __syncthreads();     // previous chunk's records fully consumed
-      if (threadIdx.x == 0) sm.n_big = 0;
-      if (threadIdx.x < 32) { sm.depth_bucket[threadIdx.x] = 0; sm.depth_cursor[threadIdx.x] = 0; }
-      __syncthreads();
-    }
-
-    // ---- stage: the chunk's triangles are dealt round-robin to the warps (entry lane*8 + warp goes
-    // to this thread) so that every warp owns a similar share of the small-triangle work.
-    const int entry = lane * kWarps + warp;
-    int x0 = 0, x1 = 0, y0 = 0, y1 = 0, n_seg = 0;
-    bool overlaps = false;
-    if (entry < n_here) {
-      const int t = list ? list[base + entry] : base + entry;
-      float4 p0, p1, p2;
-      load_triangle(verts_b, tris, t, p0, p1, p2);
-      int4 bx;
-      if (tri_boxes != nullptr) {
-        bx = unpack_box(__ldg(tri_boxes + (size_t)b * T + t));
-      } else {
-        const PixelBox pb = triangle_box(p0, p1, p2, half_w, half_h, W, H);
-        bx = make_int4(pb.left, pb.right, pb.bottom, pb.top);
-      }
-      float m[9];
-      adjugate_signed(p0.x, p1.x, p2.x, p0.y, p1.y, p2.y, p0.w, p1.w, p2.w, m);
-      sm.r0[threadIdx.x] = make_float4(m[0], m[1], m[2], __int_as_float(t));
-      sm.r1[threadIdx.x] = make_float4(m[3], m[4], m[5], p0.z);
-      sm.r2[threadIdx.x] = make_float4(m[6], m[7], m[8], p1.z);
-      sm.r3[threadIdx.x] = make_float4(p2.z, p0.w, p1.w, p2.w);
-      sm.box[threadIdx.x] = bx;
-      // Depth bound for the hierarchical z test of the big path: with all w > 0 the pixel depth
-      // (b.z)/(b.w) is a positive-weight average of z_i/w_i, so it is >= min_i z_i/w_i; the computed
-      // depth differs from the exact one by < 10 ulp of max|z_i/w_i| (three rounded barycentrics, two
-      // 3-term dot products, one division), covered by the 2^-19 relative slack.
-      float zlo = -INFINITY;
-      if (p0.w > 0.0f && p1.w > 0.0f && p2.w > 0.0f) {
-        const float d0 = p0.z / p0.w, d1 = p1.z / p1.w, d2 = p2.z / p2.w;
-        const float dabs = fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fabsf(d2));
-        zlo = fminf(fminf(d0, d1), d2) - dabs * 1.9073486e-6f - 1e-30f;
-      }
-      sm.zlo[threadIdx.x] = zlo;
-      // the box inside this tile, in tile-local pixel coordinates
-      x0 = max(bx.x, tile_x0) - tile_x0; x1 = min(bx.y, tile_x0 + kTileW) - tile_x0;
-      y0 = max(bx.z, tile_y0) - tile_y0; y1 = min(bx.w, tile_y0 + kTileH) - tile_y0;
-      overlaps = x1 > x0 && y1 > y0;
-      if (overlaps && (x1 - x0) * (y1 - y0) <= 64) n_seg = (y1 - y0) * ((x1 - x0 + 3) >> 2);
-    }
-    // ---- the warp lays the row segments of ITS small triangles out back to back (warp scan).
-    // Triangles whose segments do not fit the warp's buffer, and all large ones, take the big path.
-    const int seg_end = warp_inclusive_scan(n_seg);
-    const bool small = n_seg > 0 && seg_end <= kWarpSegCap;
-    unsigned *segs = sm.segs[warp];
-    if (small) {
-      int k = seg_end - n_seg;
-      const int per_row = (x1 - x0 + 3) >> 2;          // 1..4 segments per row
-      for (int yy = y0; yy < y1; ++yy) {
-        const unsigned head = threadIdx.x | (yy << 8);
+  for (int b0 = 0; b0 < B; b0 += kChunk) {
+    // ---- images of this slice that have candidates, in image order (every CTA builds the same list)
+    __syncthreads();
+    const bool has_work = b0 + (int)threadIdx.x < B && (!pipeline || large_count[b0 + threadIdx.x] > 0);
+    const unsigned work_votes = __ballot_sync(0xffffffffu, has_work);
+    if (lane == 0) sm.warp_count[warp] = __popc(work_votes);
+    __syncthreads();
+    int n_active = 0, my_at = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (q < per_row) segs[k + q] = head | ((x0 + 4 * q) << 12) | (min(4, x1 - x0 - 4 * q) << 16);
-        k += per_row;
-      }
-    }
-    int total_segs = small ? seg_end : 0;              // the fitting segments form a prefix
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) total_segs = max(total_segs, __shfl_xor_sync(0xffffffffu, total_segs, d));
-    // Large triangles are walked front to back (32 slices of their depth bound), which lets the
-    // hierarchical z test of the big path reject most of what lies behind the first few layers.
-    const bool is_big = overlaps && !small;
-    int slice = 0;
-    if (is_big) {
-      const float zl = sm.zlo[threadIdx.x];
-      slice = zl > -1.0f ? min(31, (int)((zl + 1.0f) * 16.0f)) : 0;
-      atomicAdd(&sm.depth_bucket[slice], 1);
-      atomicAdd(&sm.n_big, 1);
-    }
-    __syncwarp();
+    for (int k = 0; k < kWarps; ++k) { if (k == warp) my_at = n_active; n_active += sm.warp_count[k]; }
+    if (has_work) sm.active[my_at + __popc(work_votes & lanes_below)] = (unsigned short)(b0 + threadIdx.x);
+    __syncthreads();
 
-    // ---- small triangles (warp-local: no block barrier): 32 row segments per round
-    unsigned short *hits = sm.hits[warp];
-    for (int s0 = 0; s0 < total_segs; s0 += 32) {
-      // pass 1: inside test on the (up to) four pixels of this lane's segment
-      int j = 0, yy = 0, xs = 0;
-      unsigned inside = 0u;
-      if (s0 + lane < total_segs) {
-        const unsigned seg = segs[s0 + lane];
-        j = seg & 0xffu; yy = (seg >> 8) & 0xfu; xs = (seg >> 12) & 0xfu;
-        const int width = seg >> 16;
-        const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j];
-        const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
-        const float cyv = sm.cy[yy];
+  const int slice_items = n_active * macros_per_image;
+  for (; grabbed < slice_begin + slice_items; grabbed = grab_item()) {
+    const int item = grabbed - slice_begin;
+    const int ai = item / macros_per_image, macro = item - ai * macros_per_image;
+    const int b = sm.active[ai];
+    const int macro_ty = macro / macros_x, macro_tx = macro - macro_ty * macros_x;
+    const int macro_x0 = macro_tx * macro_tiles * kTileW, macro_y0 = macro_ty * macro_tiles * kTileH;
+    const int n_cand = pipeline ? large_count[b] : T;
+    const float *verts_b = verts + (size_t)b * V * 4;
+    const int32_t *cand_ids = pipeline ? large_ids + (size_t)b * T : nullptr;
+    const uint2 *cand_boxes = pipeline ? large_boxes + (size_t)b * T : nullptr;
+
+  int next = 0;              // candidates of the image scanned so far (uniform)
+  do {
+    // ---- macro list: candidates whose box touches the macro tile
+    __syncthreads();         // previous pass / item has finished with the macro list
+    if (threadIdx.x == 0) sm.n_macro = 0;
+    __syncthreads();
+    int n_macro = 0;
+    while (next < n_cand && n_macro + kScanRound <= kMacroCap) {
+      const int c0 = next + threadIdx.x, c1 = c0 + kChunk;
+      uint2 box0 = make_uint2(0u, 0u), box1 = box0;
+      bool keep0 = c0 < n_cand, keep1 = c1 < n_cand;
+      if (pipeline) {
+        if (keep0) box0 = __ldg(cand_boxes + c0);
+        if (keep1) box1 = __ldg(cand_boxes + c1);
+        keep0 = keep0 && box_touches_rect(box0, macro_x0, macro_y0, macro_tiles * kTileW, macro_tiles * kTileH);
+        keep1 = keep1 && box_touches_rect(box1, macro_x0, macro_y0, macro_tiles * kTileW, macro_tiles * kTileH);
+      }
+      const unsigned v0 = __ballot_sync(0xffffffffu, keep0), v1 = __ballot_sync(0xffffffffu, keep1);
+      int at = 0;
+      if (lane == 0 && (v0 | v1)) at = atomicAdd(&sm.n_macro, __popc(v0) + __popc(v1));
+      at = __shfl_sync(0xffffffffu, at, 0);
+      if (keep0) { const int q = at + __popc(v0 & lanes_below); sm.mslot[q] = c0; sm.mbox[q] = box0; }
+      if (keep1) { const int q = at + __popc(v0) + __popc(v1 & lanes_below); sm.mslot[q] = c1; sm.mbox[q] = box1; }
+      next += kScanRound;
+      n_macro += __syncthreads_count(keep0);               // barriers; the same totals in every thread
+      n_macro += __syncthreads_count(keep1);
+    }
+    if (n_macro == 0 && pipeline) continue;                // nothing of this range reaches the macro tile
+
+  for (int sub = 0; sub < macro_tiles * macro_tiles; ++sub) {
+    const int tile_tx = macro_tx * macro_tiles + (sub & (macro_tiles - 1)), tile_ty = macro_ty * macro_tiles + sub / macro_tiles;
+    if (tile_tx >= tiles_x || tile_ty >= tiles_y) continue;
+    const int tile_x0 = tile_tx * kTileW, tile_y0 = tile_ty * kTileH;
+    const int blk_x0 = tile_x0 + (warp & 1) * 8, blk_y0 = tile_y0 + (warp >> 1) * 4;
+    const int ix = tile_x0 + lx, iy = tile_y0 + ly;
+
+    __syncthreads();         // the previous tile's epilogue has finished with the shared arrays
+    sm.key[threadIdx.x] = kEmptyKey;
+    if (threadIdx.x < kTileW) sm.cx[threadIdx.x] = pixel_center(tile_x0 + threadIdx.x, half_w);
+    else if (threadIdx.x < kTileW + kTileH) sm.cy[threadIdx.x - kTileW] = pixel_center(tile_y0 + threadIdx.x - kTileW, half_h);
+    if (threadIdx.x == 0) { sm.n_big = 0; sm.n_cand = 0; }
+    if (threadIdx.x < 32) { sm.depth_bucket[threadIdx.x] = 0; sm.depth_cursor[threadIdx.x] = 0; }
+
+    Fragment best;
+    fragment_clear(best);
+    __syncthreads();         // publishes key / cx / cy / counters
+    const float px = sm.cx[lx], py = sm.cy[ly];
+    // pixel-centre range of this warp's 8x4 block (for the conservative edge test of the big path)
+    const float blk_px0 = sm.cx[(warp & 1) * 8], blk_px1 = sm.cx[(warp & 1) * 8 + 7];
+    const float blk_py0 = sm.cy[(warp >> 1) * 4], blk_py1 = sm.cy[(warp >> 1) * 4 + 3];
+    const float blk_pxabs = fmaxf(fabsf(blk_px0), fabsf(blk_px1)), blk_pyabs = fmaxf(fabsf(blk_py0), fabsf(blk_py1));
+    if (keys_out != nullptr && ix < W && iy < H) {
+      // pipeline mode: start from what is already drawn (small triangles, earlier passes); depth and id
+      // are all the depth rule needs, barycentrics are not produced in this mode
+      const unsigned long long seen = keys_out[((size_t)b * H + iy) * W + ix];
+      if (seen != kEmptyKey) { best.z = ordered_to_float((unsigned)(seen >> 32)); best.id = depth_key_id(seen); }
+    }
+
+    int mnext = 0;           // macro-list entries examined so far (uniform)
+    int pending = 0;         // survivors waiting in sm.cand (uniform)
+    bool first_chunk = true;
+    while (mnext < n_macro || pending > 0) {
+      // ---- filter: box-vs-tile test on 256 macro entries per round until a chunk is full (sm.cand holds
+      // up to 2 * kChunk entries: a round adds at most kChunk to fewer than kChunk)
+      while (pending < kChunk && mnext < n_macro) {
+        const int c = mnext + threadIdx.x;
+        bool keep = c < n_macro;
+        if (keep && pipeline) keep = box_touches_rect(sm.mbox[c], tile_x0, tile_y0, kTileW, kTileH);
+        const unsigned votes = __ballot_sync(0xffffffffu, keep);
+        int at = 0;
+        if (lane == 0 && votes) at = atomicAdd(&sm.n_cand, __popc(votes));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (keep) sm.cand[at + __popc(votes & lanes_below)] = (unsigned short)c;
+        mnext += kChunk;
+        pending += __syncthreads_count(keep);             // barrier; the same total in every thread
+      }
+
+      const int n_here = min(kChunk, pending);
+      if (n_here == 0) break;
+      if (!first_chunk) {
+        if (threadIdx.x == 0) sm.n_big = 0;
+        if (threadIdx.x < 32) { sm.depth_bucket[threadIdx.x] = 0; sm.depth_cursor[threadIdx.x] = 0; }
+        __syncthreads();
+      }
+      first_chunk = false;
+
+      // ---- stage: the chunk's triangles are dealt round-robin to the warps (entry lane*8 + warp goes
+      // to this thread) so that every warp owns a similar share of the small-triangle work.
+      const int entry = lane * kWarps + warp;
+      int x0 = 0, x1 = 0, y0 = 0, y1 = 0, n_seg = 0;
+      bool overlaps = false;
+      if (entry < n_here) {
+        const int mc = sm.cand[entry];
+        const int t = pipeline ? __ldg(cand_ids + sm.mslot[mc]) : sm.mslot[mc];
+        float4 p0, p1, p2;
+        load_triangle(verts_b, tris, t, p0, p1, p2);
+        int4 bx;
+        if (pipeline) {
+          bx = unpack_box(sm.mbox[mc]);
+        } else {
+          const PixelBox pb = triangle_box(p0, p1, p2, half_w, half_h, W, H);
+          bx = make_int4(pb.left, pb.right, pb.bottom, pb.top);
+        }
+        float m[9];
+        adjugate_signed(p0.x, p1.x, p2.x, p0.y, p1.y, p2.y, p0.w, p1.w, p2.w, m);
+        sm.r0[threadIdx.x] = make_float4(m[0], m[1], m[2], __int_as_float(t));
+        sm.r1[threadIdx.x] = make_float4(m[3], m[4], m[5], p0.z);
+        sm.r2[threadIdx.x] = make_float4(m[6], m[7], m[8], p1.z);
+        sm.r3[threadIdx.x] = make_float4(p2.z, p0.w, p1.w, p2.w);
+        sm.box[threadIdx.x] = bx;
+        // Depth bound for the hierarchical z test of the big path: with all w > 0 the pixel depth
+        // (b.z)/(b.w) is a positive-weight average of z_i/w_i, so it is >= min_i z_i/w_i; the computed
+        // depth differs from the exact one by < 10 ulp of max|z_i/w_i| (three rounded barycentrics, two
+        // 3-term dot products, one division), covered by the 2^-19 relative slack.
+        float zlo = -INFINITY;
+        if (p0.w > 0.0f && p1.w > 0.0f && p2.w > 0.0f) {
+          const float d0 = p0.z / p0.w, d1 = p1.z / p1.w, d2 = p2.z / p2.w;
+          const float dabs = fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fabsf(d2));
+          zlo = fminf(fminf(d0, d1), d2) - dabs * 1.9073486e-6f - 1e-30f;
+        }
+        sm.zlo[threadIdx.x] = zlo;
+        // the box inside this tile, in tile-local pixel coordinates
+        x0 = max(bx.x, tile_x0) - tile_x0; x1 = min(bx.y, tile_x0 + kTileW) - tile_x0;
+        y0 = max(bx.z, tile_y0) - tile_y0; y1 = min(bx.w, tile_y0 + kTileH) - tile_y0;
+        overlaps = x1 > x0 && y1 > y0;
+        if (overlaps && (x1 - x0) * (y1 - y0) <= 64) n_seg = (y1 - y0) * ((x1 - x0 + 3) >> 2);
+      }
+      // ---- the warp lays the row segments of ITS small triangles out back to back (warp scan).
+      // Triangles whose segments do not fit the warp's buffer, and all large ones, take the big path.
+      const int seg_end = warp_inclusive_scan(n_seg);
+      const bool small = n_seg > 0 && seg_end <= kWarpSegCap;
+      unsigned *segs = sm.segs[warp];
+      if (small) {
+        int k = seg_end - n_seg;
+        const int per_row = (x1 - x0 + 3) >> 2;          // 1..4 segments per row
+        for (int yy = y0; yy < y1; ++yy) {
+          const unsigned head = threadIdx.x | (yy << 8);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float e[3], esum;
-          edge_values(m, sm.cx[(xs + k) & (kTileW - 1)], cyv, e);
-          if (edges_inside(e, esum) && k < width) inside |= 1u << k;
+          for (int q = 0; q < 4; ++q)
+            if (q < per_row) segs[k + q] = head | ((x0 + 4 * q) << 12) | (min(4, x1 - x0 - 4 * q) << 16);
+          k += per_row;
         }
       }
-      // compact the inside pixels of the warp and deal them to the lanes again
-      const int mine = __popc(inside);
-      const int upto = warp_inclusive_scan(mine);
-      const int n_hits = __shfl_sync(0xffffffffu, upto, 31);
-      int at = upto - mine;
-      while (inside) {
-        const int k = __ffs(inside) - 1;
-        inside &= inside - 1;
-        hits[at++] = (unsigned short)((j << 8) | (yy * kTileW + xs + k));
-      }
-      __syncwarp();
-      // pass 2: barycentrics / depth for exactly those pixels, depth resolve by packed atomicMin
-      for (int h = lane; h < n_hits; h += 32) {
-        const unsigned hit = hits[h];
-        const int jj = hit >> 8, pix = hit & 0xffu;
-        const float4 q0 = sm.r0[jj], q1 = sm.r1[jj], q2 = sm.r2[jj], q3 = sm.r3[jj];
-        const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
-        const float zc[3] = {q1.w, q2.w, q3.x};
-        const float wc[3] = {q3.y, q3.z, q3.w};
-        float e[3], esum, bc[3], z;
-        edge_values(m, sm.cx[pix & (kTileW - 1)], sm.cy[pix >> kTileShiftX], e);
-        edges_inside(e, esum);
-        if (fragment_depth(e, esum, zc, wc, bc, z))
-          atomicMin(&sm.key[pix], depth_key(z, __float_as_int(q0.w)));
-      }
-      __syncwarp();
-    }
-
-    // ---- big triangles: warp per 8x4 block, ballot cull, lane per pixel (needs everyone's records)
-    __syncthreads();
-    const int n_big = sm.n_big;
-    if (n_big > 0) {
-      // exclusive prefix of the slice counts (every warp computes it for itself), then placement
-      const int count = sm.depth_bucket[lane];
-      const int start = warp_inclusive_scan(count) - count;
-      const int my_start = __shfl_sync(0xffffffffu, start, slice);
-      if (is_big) sm.big_list[my_start + atomicAdd(&sm.depth_cursor[slice], 1)] = (unsigned short)threadIdx.x;
-      __syncthreads();
-    }
-    for (int g0 = 0; g0 < n_big; g0 += 32) {
-      // Farthest depth any pixel of this warp's block currently holds (1.0 while a pixel is empty):
-      // a triangle whose depth bound lies beyond it cannot change the block (K.cpp:401 rejects z > zbuf).
-      const float block_zmax = ordered_to_float(__reduce_max_sync(0xffffffffu, float_to_ordered(best.z)));
-      bool touches = false;
-      if (g0 + lane < n_big) {
-        const int jj = sm.big_list[g0 + lane];
-        const int4 bx = sm.box[jj];
-        touches = bx.x < blk_x0 + 8 && bx.y > blk_x0 && bx.z < blk_y0 + 4 && bx.w > blk_y0 &&
-                  sm.zlo[jj] <= block_zmax;
-        if (touches) {
-          // Conservative edge test: an edge function is linear, so its largest exact value over the
-          // block's pixel centres sits at a corner; the fp32 evaluation at any pixel is within
-          // 3 ulp-sums of it, the corner evaluation too.  If even that bound is negative for one edge,
-          // no pixel of the block can pass the inside test (K.cpp:93-98).
-          const float4 q0 = sm.r0[jj], q1 = sm.r1[jj], q2 = sm.r2[jj];
-          const float ea[3] = {q0.x, q1.x, q2.x}, eb[3] = {q0.y, q1.y, q2.y}, ec[3] = {q0.z, q1.z, q2.z};
+      int total_segs = small ? seg_end : 0;              // the fitting segments form a prefix
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const float hi = ea[i] * (ea[i] >= 0.0f ? blk_px1 : blk_px0) + eb[i] * (eb[i] >= 0.0f ? blk_py1 : blk_py0) + ec[i];
-            const float mag = fabsf(ea[i]) * blk_pxabs + fabsf(eb[i]) * blk_pyabs + fabsf(ec[i]);
-            if (hi < -9.5367432e-7f * mag) touches = false;             // 2^-20 = 16 ulp of the magnitude sum
+      for (int d = 16; d > 0; d >>= 1) total_segs = max(total_segs, __shfl_xor_sync(0xffffffffu, total_segs, d));
+      // Large triangles are walked front to back (32 slices of their depth bound), which lets the
+      // hierarchical z test of the big path reject most of what lies behind the first few layers.
+      const bool is_big = overlaps && !small;
+      int slice = 0;
+      if (is_big) {
+        const float zl = sm.zlo[threadIdx.x];
+        slice = zl > -1.0f ? min(31, (int)((zl + 1.0f) * 16.0f)) : 0;
+        atomicAdd(&sm.depth_bucket[slice], 1);
+        atomicAdd(&sm.n_big, 1);
+      }
+      __syncwarp();
+
+      // ---- small triangles (warp-local: no block barrier): 32 row segments per round
+      unsigned short *hits = sm.hits[warp];
+      for (int s0 = 0; s0 < total_segs; s0 += 32) {
+        // pass 1: inside test on the (up to) four pixels of this lane's segment
+        int j = 0, yy = 0, xs = 0;
+        unsigned inside = 0u;
+        if (s0 + lane < total_segs) {
+          const unsigned seg = segs[s0 + lane];
+          j = seg & 0xffu; yy = (seg >> 8) & 0xfu; xs = (seg >> 12) & 0xfu;
+          const int width = seg >> 16;
+          const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j];
+          const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
+          const float cyv = sm.cy[yy];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float e[3], esum;
+            edge_values(m, sm.cx[(xs + k) & (kTileW - 1)], cyv, e);
+            if (edges_inside(e, esum) && k < width) inside |= 1u << k;
           }
         }
-      }
-      unsigned todo = __ballot_sync(0xffffffffu, touches);
-      while (todo) {
-        const int j = sm.big_list[g0 + __ffs(todo) - 1];
-        todo &= todo - 1;
-        const int4 bx = sm.box[j];
-        // The reference only visits pixels inside the triangle's own box (K.cpp:374-375).
-        if (ix >= bx.x && ix < bx.y && iy >= bx.z && iy < bx.w) {
-          const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j], q3 = sm.r3[j];
+        // compact the inside pixels of the warp and deal them to the lanes again
+        const int mine = __popc(inside);
+        const int upto = warp_inclusive_scan(mine);
+        const int n_hits = __shfl_sync(0xffffffffu, upto, 31);
+        int at = upto - mine;
+        while (inside) {
+          const int k = __ffs(inside) - 1;
+          inside &= inside - 1;
+          hits[at++] = (unsigned short)((j << 8) | (yy * kTileW + xs + k));
+        }
+        __syncwarp();
+        // pass 2: barycentrics / depth for exactly those pixels, depth resolve by packed atomicMin
+        for (int h = lane; h < n_hits; h += 32) {
+          const unsigned hit = hits[h];
+          const int jj = hit >> 8, pix = hit & 0xffu;
+          const float4 q0 = sm.r0[jj], q1 = sm.r1[jj], q2 = sm.r2[jj], q3 = sm.r3[jj];
           const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
           const float zc[3] = {q1.w, q2.w, q3.x};
           const float wc[3] = {q3.y, q3.z, q3.w};
-          fragment_test(m, zc, wc, px, py, __float_as_int(q0.w), best);
+          float e[3], esum, bc[3], z;
+          edge_values(m, sm.cx[pix & (kTileW - 1)], sm.cy[pix >> kTileShiftX], e);
+          edges_inside(e, esum);
+          if (fragment_depth(e, esum, zc, wc, bc, z))
+            atomicMin(&sm.key[pix], depth_key(z, __float_as_int(q0.w)));
+        }
+        __syncwarp();
+      }
+
+      // ---- big triangles: warp per 8x4 block, ballot cull, lane per pixel (needs everyone's records)
+      __syncthreads();
+      const int n_big = sm.n_big;
+      if (n_big > 0) {
+        // exclusive prefix of the slice counts (every warp computes it for itself), then placement
+        const int count = sm.depth_bucket[lane];
+        const int start = warp_inclusive_scan(count) - count;
+        const int my_start = __shfl_sync(0xffffffffu, start, slice);
+        if (is_big) sm.big_list[my_start + atomicAdd(&sm.depth_cursor[slice], 1)] = (unsigned short)threadIdx.x;
+        __syncthreads();
+      }
+      for (int g0 = 0; g0 < n_big; g0 += 32) {
+        // Farthest depth any pixel of this warp's block currently holds (1.0 while a pixel is empty):
+        // a triangle whose depth bound lies beyond it cannot change the block (K.cpp:401 rejects z > zbuf).
+        const float block_zmax = ordered_to_float(__reduce_max_sync(0xffffffffu, float_to_ordered(best.z)));
+        bool touches = false;
+        if (g0 + lane < n_big) {
+          const int jj = sm.big_list[g0 + lane];
+          const int4 bx = sm.box[jj];
+          touches = bx.x < blk_x0 + 8 && bx.y > blk_x0 && bx.z < blk_y0 + 4 && bx.w > blk_y0 &&
+                    sm.zlo[jj] <= block_zmax;
+          if (touches) {
+            // Conservative edge test: an edge function is linear, so its largest exact value over the
+            // block's pixel centres sits at a corner; the fp32 evaluation at any pixel is within
+            // 3 ulp-sums of it, the corner evaluation too.  If even that bound is negative for one edge,
+            // no pixel of the block can pass the inside test (K.cpp:93-98).
+            const float4 q0 = sm.r0[jj], q1 = sm.r1[jj], q2 = sm.r2[jj];
+            const float ea[3] = {q0.x, q1.x, q2.x}, eb[3] = {q0.y, q1.y, q2.y}, ec[3] = {q0.z, q1.z, q2.z};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const float hi = ea[i] * (ea[i] >= 0.0f ? blk_px1 : blk_px0) + eb[i] * (eb[i] >= 0.0f ? blk_py1 : blk_py0) + ec[i];
+              const float mag = fabsf(ea[i]) * blk_pxabs + fabsf(eb[i]) * blk_pyabs + fabsf(ec[i]);
+              if (hi < -9.5367432e-7f * mag) touches = false;             // 2^-20 = 16 ulp of the magnitude sum
+            }
+          }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, touches);
+        while (todo) {
+          const int j = sm.big_list[g0 + __ffs(todo) - 1];
+          todo &= todo - 1;
+          const int4 bx = sm.box[j];
+          // The reference only visits pixels inside the triangle's own box (K.cpp:374-375).
+          if (ix >= bx.x && ix < bx.y && iy >= bx.z && iy < bx.w) {
+            const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j], q3 = sm.r3[j];
+            const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
+            const float zc[3] = {q1.w, q2.w, q3.x};
+            const float wc[3] = {q3.y, q3.z, q3.w};
+            fragment_test(m, zc, wc, px, py, __float_as_int(q0.w), best);
+          }
         }
       }
+      __syncthreads();         // the chunk's records and candidate entries are consumed
+      // survivors beyond this chunk move to the front of the filter list
+      const int left = pending - n_here;
+      unsigned short moved = 0;
+      if ((int)threadIdx.x < left) moved = sm.cand[kChunk + threadIdx.x];
+      __syncthreads();
+      if ((int)threadIdx.x < left) sm.cand[threadIdx.x] = moved;
+      if (threadIdx.x == 0) sm.n_cand = left;
+      pending = left;
+      __syncthreads();
     }
-  }
-  __syncthreads();           // all keys final; record planes dead from here on
 
-  // ---- resolve: minimum of the two paths
-  const unsigned long long key_small = sm.key[ly * kTileW + lx];
-  const unsigned long long key_big = best.id >= 0 ? depth_key(best.z, best.id) : kEmptyKey;
-  if (keys_out != nullptr) {
-    // large-triangle pass of the binned pipeline: merge into the global keys (this CTA is the only
-    // writer of its pixels now; the scatter kernel has finished), resolve_kernel does the rest.
-    if (ix < W && iy < H) {
-      const size_t p = ((size_t)b * H + iy) * W + ix;
-      const unsigned long long mine = min(key_small, key_big);
-      if (mine < keys_out[p]) keys_out[p] = mine;
+    // ---- resolve: minimum of the two paths (all keys final; record planes dead from here on)
+    const unsigned long long key_small = sm.key[ly * kTileW + lx];
+    const unsigned long long key_big = best.id >= 0 ? depth_key(best.z, best.id) : kEmptyKey;
+    if (keys_out != nullptr) {
+      // large-triangle pass of the pipeline: merge into the global keys (this CTA is the only
+      // writer of its pixels now; the scatter kernel has finished), resolve_kernel does the rest.
+      if (ix < W && iy < H) {
+        const size_t p = ((size_t)b * H + iy) * W + ix;
+        const unsigned long long mine = min(key_small, key_big);
+        if (mine < keys_out[p]) keys_out[p] = mine;
+      }
+      continue;
     }
-    return;
-  }
-  if (key_small < key_big) {     // the winner came through the key buffer: re-evaluate it once
-    const int t = depth_key_id(key_small);
-    float4 p0, p1, p2;
-    load_triangle(verts_b, tris, t, p0, p1, p2);
-    evaluate_winner(p0, p1, p2, px, py, t, best);
-  }
-  float *stage = reinterpret_cast<float *>(sm.r0) + warp * (32 * 16);
-  block_epilogue<A_STATIC>(stage, b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
-                           out_ids, out_bary, out_z, out_image);
+    if (key_small < key_big) {     // the winner came through the key buffer: re-evaluate it once
+      const int t = depth_key_id(key_small);
+      float4 p0, p1, p2;
+      load_triangle(verts_b, tris, t, p0, p1, p2);
+      evaluate_winner(p0, p1, p2, px, py, t, best);
+    }
+    float *stage = reinterpret_cast<float *>(sm.r0) + warp * (32 * 16);
+    block_epilogue<A_STATIC>(stage, b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
+                             out_ids, out_bary, out_z, out_image);
+  }                          // tiles of the macro tile
+  } while (next < n_cand);   // passes over the image's candidates
+  }                          // work items
+  slice_begin += slice_items;
+  }                          // image slices
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -584,9 +641,9 @@ struct ScatterWarpSmem {
 
 __global__ void __launch_bounds__(kScatterWarps * 32)
 scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int T, int W, int H,
-                     float half_w, float half_h, int tiles_x, int tiles_per_image,
-                     const float *__restrict__ centers, uint2 *__restrict__ tri_boxes,
-                     int *__restrict__ tile_counts, unsigned long long *__restrict__ keys) {
+                     float half_w, float half_h, const float *__restrict__ centers,
+                     int *__restrict__ large_count, int32_t *__restrict__ large_ids,
+                     uint2 *__restrict__ large_boxes, unsigned long long *__restrict__ keys) {
   __shared__ __align__(16) ScatterWarpSmem sm_all[kScatterWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ScatterWarpSmem &sm = sm_all[warp];
@@ -598,6 +655,7 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
   // ---- setup: one triangle per lane
   int n_seg = 0, bw = 0, bh = 0;
   uint2 big_box = make_uint2(0u, 0u);
+  bool is_large = false;
   if (t < T) {
     float4 p0, p1, p2;
     load_triangle(verts + (size_t)b * V * 4, tris, t, p0, p1, p2);
@@ -615,13 +673,21 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
         n_seg = bh * ((bw + 3) >> 2);
       } else {
         big_box = pack_box(box);
+        is_large = true;
       }
     }
-    tri_boxes[(size_t)b * T + t] = big_box;            // empty for small triangles: bin_fill skips them
   }
-  // large triangles are only counted into the tiles they touch (raster_tile_kernel draws them)
-  int *counts = tile_counts + (size_t)b * tiles_per_image;
-  for_each_tile(big_box, tiles_x, [&](int tile, int) { atomicAdd(counts + tile, 1); });
+  // large triangles go to the image's large list (raster_tile_kernel draws them); one atomic per warp
+  const unsigned large_votes = __ballot_sync(0xffffffffu, is_large);
+  if (large_votes) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(large_count + b, __popc(large_votes));
+    slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(large_votes & ((1u << lane) - 1u));
+    if (is_large) {
+      large_ids[(size_t)b * T + slot] = t;
+      large_boxes[(size_t)b * T + slot] = big_box;
+    }
+  }
 
   // pass 2 of the scatter: barycentrics / depth of queued inside pixels, depth resolve by packed
   // atomicMin in global memory (L2).  Lane h of the warp takes queue entry first + h.
@@ -780,18 +846,28 @@ interpolate_kernel(const float *__restrict__ attrs, const int32_t *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 
 static int launch_raster(Context *ctx, const float *verts, const int32_t *tris, int B, int V, int T,
-                         int W, int H, const int *counts, const int *offsets, const int32_t *lists,
-                         const uint2 *boxes, int32_t *ids, float *bary, float *z, const float *attrs, const float *bg, int A,
+                         int W, int H, int *work_cursor, const int *large_count, const int32_t *large_ids, const uint2 *large_boxes,
+                         int32_t *ids, float *bary, float *z, const float *attrs, const float *bg, int A,
                          float *image, unsigned long long *keys_out, cudaStream_t stream) {
   const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
-  const int tiles = tiles_x * tiles_y;
   const float half_w = (float)(0.5 * W), half_h = (float)(0.5 * H);   // K.cpp:309-310
-  dim3 grid(tiles_x, tiles_y, B);
+  // persistent CTAs: 4 per SM (launch bounds), fewer when there is less work than that.  Macro tiles of
+  // 4x4 screen tiles amortise the candidate scan 16-fold; small jobs use smaller ones to keep every SM busy.
+  const long long resident = (long long)ctx->sm_count * 4;
+  int macro_tiles = kMacroTiles;
+  long long n_items = 0;
+  for (;; macro_tiles >>= 1) {
+    n_items = (long long)B * ((tiles_x + macro_tiles - 1) / macro_tiles) * ((tiles_y + macro_tiles - 1) / macro_tiles);
+    if (macro_tiles == 1 || n_items >= 4 * resident) break;
+  }
+  if (n_items > (long long)INT_MAX / 2) return set_error(ctx, PMR_ERR_SIZE, "too many screen tiles");
+  const int grid = (int)(n_items < resident ? n_items : resident);
   StageScope timed(ctx, PMR_STAGE_RASTER, stream);
 #define PMR_LAUNCH(AS)                                                                              \
-  raster_tile_kernel<AS><<<grid, kChunk, 0, stream>>>(verts, tris, V, T, W, H, half_w, half_h,      \
-                                                     tiles, counts, offsets, lists, boxes, ids,     \
-                                                     bary, z, attrs, bg, A, image, keys_out)
+  raster_tile_kernel<AS><<<grid, kChunk, 0, stream>>>(verts, tris, B, V, T, W, H, half_w, half_h,   \
+                                                     tiles_x, tiles_y, macro_tiles, work_cursor,    \
+                                                     large_count, large_ids,                        \
+                                                     large_boxes, ids, bary, z, attrs, bg, A, image, keys_out)
   if (image == nullptr || keys_out != nullptr) PMR_LAUNCH(0);
   else if (A == 4) PMR_LAUNCH(4);
   else if (A == 9) PMR_LAUNCH(9);
@@ -807,18 +883,18 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
                  int32_t *ids, float *bary, float *z, const float *attrs, const float *bg, int A,
                  float *image, cudaStream_t stream) {
   if (B == 0 || W == 0 || H == 0) return PMR_OK;
-  const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
-  const int tiles = tiles_x * tiles_y;
   const float half_w = (float)(0.5 * W), half_h = (float)(0.5 * H);
 
-  if (T <= ctx->small_mesh_threshold) {
+  if (T <= ctx->small_mesh_threshold && T <= kTinyMeshMax) {
     // tiny mesh: one kernel, every tile walks all triangles and writes the outputs itself
-    return launch_raster(ctx, verts, tris, B, V, T, W, H, nullptr, nullptr, nullptr, nullptr, ids, bary, z, attrs,
-                         bg, A, image, nullptr, stream);
+    int rc0 = ctx->bins.reserve(ctx, 16);
+    if (rc0) return rc0;
+    PMR_CUDA(ctx, cudaMemsetAsync(ctx->bins.ptr, 0, 16, stream));       // the work counter
+    return launch_raster(ctx, verts, tris, B, V, T, W, H, (int *)ctx->bins.ptr, nullptr, nullptr, nullptr, ids, bary, z,
+                         attrs, bg, A, image, nullptr, stream);
   }
 
-  const size_t n_tiles = (size_t)B * tiles, n_pixels = (size_t)B * H * W;
-  if (n_tiles > (size_t)INT_MAX) return set_error(ctx, PMR_ERR_SIZE, "too many screen tiles");
+  const size_t n_pixels = (size_t)B * H * W;
   int rc;
   // pixel-centre table of this image size (rebuilt only when the size changes)
   if (ctx->centers_w != W || ctx->centers_h != H) {
@@ -829,60 +905,39 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
     ctx->centers_w = W; ctx->centers_h = H;
   }
   const float *centers = (const float *)ctx->centers.ptr;
-  // workspace: [total u64 | counts | cursors | offsets | boxes], keys
-  rc = ctx->bins.reserve(ctx, 16 + n_tiles * 3 * sizeof(int) + (size_t)B * T * sizeof(uint2) + 64);
+  // workspace: [work cursor | large_count[B] | pad to 16 | large_boxes[B*T] (8 B) | large_ids[B*T]], keys
+  const size_t count_bytes = (((size_t)(B + 1) * sizeof(int)) + 15) & ~(size_t)15;
+  rc = ctx->bins.reserve(ctx, count_bytes + (size_t)B * T * (sizeof(uint2) + sizeof(int32_t)));
   if (rc) return rc;
   rc = ctx->keys.reserve(ctx, n_pixels * sizeof(unsigned long long));
   if (rc) return rc;
   char *base = (char *)ctx->bins.ptr;
-  unsigned long long *total = (unsigned long long *)base;
-  int *counts = (int *)(base + 16);
-  int *cursors = counts + n_tiles;
-  int *offsets = cursors + n_tiles;
-  uint2 *boxes = (uint2 *)(((uintptr_t)(offsets + n_tiles) + 15) & ~(uintptr_t)15);
+  int *work_cursor = (int *)base;
+  int *large_count = work_cursor + 1;
+  uint2 *large_boxes = (uint2 *)(base + count_bytes);
+  int32_t *large_ids = (int32_t *)(large_boxes + (size_t)B * T);
   unsigned long long *keys = (unsigned long long *)ctx->keys.ptr;
+  ctx->last_large_count = large_count;
+  ctx->last_large_images = B;
 
   {
     StageScope timed(ctx, PMR_STAGE_BIN, stream);
-    PMR_CUDA(ctx, cudaMemsetAsync(base, 0, 16 + n_tiles * 2 * sizeof(int), stream));
+    PMR_CUDA(ctx, cudaMemsetAsync(work_cursor, 0, (size_t)(B + 1) * sizeof(int), stream));
     PMR_CUDA(ctx, cudaMemsetAsync(keys, 0xff, n_pixels * sizeof(unsigned long long), stream));   // kEmptyKey
   }
   {
     StageScope timed(ctx, PMR_STAGE_SCATTER, stream);
     scatter_small_kernel<<<dim3((T + kScatterWarps * 32 - 1) / (kScatterWarps * 32), B), kScatterWarps * 32, 0, stream>>>(
-        verts, tris, V, T, W, H, half_w, half_h, tiles_x, tiles, centers, boxes, counts, keys);
+        verts, tris, V, T, W, H, half_w, half_h, centers, large_count, large_ids, large_boxes, keys);
     ctx->launches += 1;
     rc = check_launch(ctx, "scatter_small_kernel");
     if (rc) return rc;
   }
-  unsigned long long n_entries = 0;
-  {
-    StageScope timed(ctx, PMR_STAGE_BIN, stream);
-    bin_offsets_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(counts, (int)n_tiles, offsets, total);
-    ctx->launches += 1;
-    rc = check_launch(ctx, "bin_offsets_kernel");
-    if (rc) return rc;
-    // The list length of the large triangles is data dependent: read it back (8 bytes, pinned).
-    PMR_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-    PMR_CUDA(ctx, cudaStreamSynchronize(stream));
-    n_entries = *ctx->mailbox;
-    ctx->last_bin_entries = n_entries;
-    if (n_entries >= (1ull << 31)) return set_error(ctx, PMR_ERR_SIZE, "tile lists exceed 2^31 entries");
-    if (n_entries > 0) {
-      rc = ctx->lists.reserve(ctx, (size_t)(n_entries + 1) * sizeof(int32_t));
-      if (rc) return rc;
-      bin_fill_kernel<<<dim3((T + 255) / 256, B), 256, 0, stream>>>(boxes, T, tiles_x, tiles, offsets, cursors,
-                                                                    (int32_t *)ctx->lists.ptr);
-      ctx->launches += 1;
-      rc = check_launch(ctx, "bin_fill_kernel");
-      if (rc) return rc;
-    }
-  }
-  if (n_entries > 0) {
-    rc = launch_raster(ctx, verts, tris, B, V, T, W, H, counts, offsets, (const int32_t *)ctx->lists.ptr, boxes,
-                       ids, bary, z, attrs, bg, A, image, keys, stream);
-    if (rc) return rc;
-  }
+  // Large triangles: always launched (how many there are is only known on the device); CTAs of images
+  // without large triangles fall through their tiles in a few hundred nanoseconds each.
+  rc = launch_raster(ctx, verts, tris, B, V, T, W, H, work_cursor, large_count, large_ids, large_boxes,
+                     ids, bary, z, attrs, bg, A, image, keys, stream);
+  if (rc) return rc;
   {
     StageScope timed(ctx, PMR_STAGE_RESOLVE, stream);
     dim3 grid((W + 15) / 16, (H + 2 * kResolveWarps - 1) / (2 * kResolveWarps), B);
