@@ -4,11 +4,12 @@
 
 One "step" = one pass of the hot path over one batch: fused rasterize+interpolate forward
 (ids, barycentrics, z, attribute image) and its backward (gradients to clip-space vertices and
-attributes), A = 9 attributes.  N = 1 runs BASELINE.json configs[1] (c2: 50 244-triangle UV sphere,
-64 views x 512^2).  N > 1: one process per GPU (torchrun), every rank runs the same per-GPU batch
-(weak scaling), the views share one mesh, so each step ends with the on-device reduction of the
-per-view clip-space gradients to one world-space [V,3] gradient and ONE NCCL all-reduce of it
-(SURVEY.md section 8e); value = pixels of all ranks / max-over-ranks time.
+attributes), A = 9 attributes.  The default workload is BASELINE.json configs[1] (c2: 50 244-triangle
+UV sphere, 64 views x 512^2 per GPU).  The views of the sphere configs share one world-space mesh, so
+a step is: world -> clip for the rank's views (one kernel), rasterize+interpolate forward, backward,
+reduction of the per-view clip-space gradients to one world-space [V,3] gradient (one kernel) and,
+for N > 1 (one process per GPU under torchrun, the same per-GPU batch on every rank: weak scaling),
+ONE NCCL all-reduce of it; value = pixels of all ranks / max-over-ranks time.
 
 Prints ONE JSON line (rank 0).  --impl reference times the reference's own CPU implementation
 (oracle/_ref kernel + the reference's torch-op interpolation chain) on the host cores instead.
@@ -70,9 +71,11 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, index, period_ms=10):
+    def __init__(self, index, period_ms=20):
         import subprocess
         self.proc = None
+        if index is None:
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
@@ -183,10 +186,12 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     sc = make_workload(args.config, args.batch)
-    shared_mesh = world > 1 and "world_vertices" in sc and sc["world_vertices"].ndim == 2
+    shared_mesh = "world_vertices" in sc and sc["world_vertices"].ndim == 2
     if shared_mesh:
         # Weak scaling: the job renders world * B views of ONE mesh; this rank owns a contiguous slice.
         from pytorch_mesh_renderer_b200 import distributed as D
@@ -230,7 +235,7 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(local_rank if rank == 0 else None)   # one sampler per job, not per rank
         sampler.start()
         _lib.enable_stage_timing(local_rank, True)
         _lib.read_stage_timing(local_rank, reset=True)
@@ -350,7 +355,8 @@ def main():
                        "image": [H, W], "attributes": A, "backward_mode": args.mode,
                        "triangles_per_s": world * B * T / (ms_step * 1e-3),
                        "l2": "per-step working set %.2f GB exceeds the 126 MB L2; no explicit flush" % ((bytes_fwd + bytes_bwd) / 1e9),
-                       "collective": "all_reduce(sum) of world-space vertex gradient [V,3] per step" if shared_mesh else "none"},
+                       "vertex_stage": "world->clip kernel + view-summed backward inside the step" if shared_mesh else "none",
+                       "collective": "all_reduce(sum) of world-space vertex gradient [V,3] per step" if (shared_mesh and world > 1) else "none"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
