@@ -38,8 +38,10 @@ struct Context {
   int small_mesh_threshold = 64;      // T at or below this: no binning, every tile walks all triangles
   Buffer bins, scratch, keys, centers;
   int centers_w = -1, centers_h = -1;  // image size the pixel-centre table was built for
-  cudaStream_t copy_stream = nullptr;       // host entry point: uploads the image gradient while the forward runs
-  cudaEvent_t copy_done = nullptr, call_begin = nullptr;
+  // host entry point: uploads and downloads run on their own streams beside the caller's (kernels)
+  cudaStream_t copy_stream = nullptr, down_stream = nullptr;
+  cudaEvent_t call_begin = nullptr;
+  std::vector<cudaEvent_t> host_events;     // per slice: inputs up, gradient up, forward done, backward done
   const int *last_large_count = nullptr;    // device: large triangles per image of the last pipeline forward
   int last_large_images = 0;
   long long launches = 0;             // kernels launched through this context (bench gpu_launches)
