@@ -90,7 +90,8 @@ PMR_API int pmr_set_small_mesh_threshold(pmr_context *ctx, int triangles);
 #define PMR_STAGE_INTERP 3   /* standalone interpolate_kernel */
 #define PMR_STAGE_SCATTER 4  /* scatter_small_kernel (small triangles -> depth keys; lists the large ones) */
 #define PMR_STAGE_RESOLVE 5  /* resolve_kernel (depth keys -> ids / bary / z / interpolated image) */
-#define PMR_STAGE_COUNT 6
+#define PMR_STAGE_SHADE 6    /* shade_diffuse kernels (the Phong caller of the path) */
+#define PMR_STAGE_COUNT 7
 PMR_API int pmr_enable_stage_timing(pmr_context *ctx, int enable);
 PMR_API int pmr_read_stage_timing(pmr_context *ctx, double *ms, long long *counts, int reset);
 
@@ -167,6 +168,25 @@ PMR_API int pmr_transform_forward(pmr_context *ctx, const float *matrices, const
                                   int B, int V, int shared, float *clip_vertices, void *stream);
 PMR_API int pmr_transform_backward(pmr_context *ctx, const float *matrices, const float *d_clip_vertices,
                                    int B, int V, int shared, float *d_world_vertices, void *stream);
+
+/*
+ * Direct caller of the path: per-pixel Phong lighting, diffuse + ambient terms, of the interpolated
+ * attribute image (reference src/mesh_renderer/render.py:201-228 + phong_shader :231-386 for a
+ * `render` call without specular colours).  pixels float32 [B,H,W,A], A >= 9, channels
+ * [normal xyz, world position xyz, diffuse rgb] (render.py:181); light_positions / light_intensities
+ * float32 [B,L,3], L <= 16; ambient float32 [B,3] or NULL.  rgba float32 [B,H,W,4] (16-byte aligned),
+ * rows flipped (row 0 = top of the image, render.py:382-386), alpha = 1 where the diffuse colour is not
+ * the -1 background.  The backward maps grad_rgba to d_pixels [B,H,W,A] (channels beyond 8 get zero);
+ * gradients with respect to the lights are not produced.
+ */
+PMR_API int pmr_shade_diffuse_forward(pmr_context *ctx, const float *pixels, const float *light_positions,
+                                      const float *light_intensities, const float *ambient,
+                                      int B, int L, int A, int image_width, int image_height,
+                                      float *rgba, void *stream);
+PMR_API int pmr_shade_diffuse_backward(pmr_context *ctx, const float *grad_rgba, const float *pixels,
+                                       const float *light_positions, const float *light_intensities,
+                                       const float *ambient, int B, int L, int A, int image_width,
+                                       int image_height, float *d_pixels, void *stream);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,8 @@ _PROTOTYPES = {
                                                           _vp, _vp, _i, _vp]),
     "pmr_transform_forward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "pmr_transform_backward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "pmr_shade_diffuse_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pmr_shade_diffuse_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pmr_rasterize_clip_space_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                                                      _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
 }
@@ -71,7 +73,7 @@ class PmrError(RuntimeError):
 
 
 def context(device_index):
-    """One library context (workspace, pinned mailbox) per CUDA device, created lazily."""
+    """One library context (device workspace) per CUDA device, created lazily."""
     with _lock:
         ctx = _contexts.get(device_index)
         if ctx is None:
@@ -113,7 +115,7 @@ def launch_count(device_index=None):
     return lib.pmr_launch_count(c) if c is not None else 0
 
 
-STAGES = ("bin", "raster", "backward", "interp", "scatter", "resolve")
+STAGES = ("bin", "raster", "backward", "interp", "scatter", "resolve", "shade")
 
 
 def enable_stage_timing(device_index, on=True):

@@ -385,4 +385,32 @@ int pmr_transform_backward(pmr_context *ctx, const float *matrices, const float 
                                       (cudaStream_t)stream);
 }
 
+int pmr_shade_diffuse_forward(pmr_context *ctx, const float *pixels, const float *light_positions,
+                              const float *light_intensities, const float *ambient, int B, int L, int A, int W,
+                              int H, float *rgba, void *stream) {
+  int rc = pmr::validate_common(ctx, B, 0, 0, W, H);
+  if (rc) return rc;
+  if (A < 9 || L < 0) return set_error(ctx, PMR_ERR_INVALID, "shading needs at least 9 pixel channels and L >= 0");
+  if (B == 0) return PMR_OK;
+  if (!pixels || !rgba || (L > 0 && (!light_positions || !light_intensities)))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(rgba)) return set_error(ctx, PMR_ERR_INVALID, "rgba must be 16-byte aligned");
+  return pmr::shade_diffuse_forward_impl(ctx, pixels, light_positions, light_intensities, ambient, B, L, A, W, H, rgba,
+                                         (cudaStream_t)stream);
+}
+
+int pmr_shade_diffuse_backward(pmr_context *ctx, const float *grad_rgba, const float *pixels,
+                               const float *light_positions, const float *light_intensities, const float *ambient,
+                               int B, int L, int A, int W, int H, float *d_pixels, void *stream) {
+  int rc = pmr::validate_common(ctx, B, 0, 0, W, H);
+  if (rc) return rc;
+  if (A < 9 || L < 0) return set_error(ctx, PMR_ERR_INVALID, "shading needs at least 9 pixel channels and L >= 0");
+  if (B == 0) return PMR_OK;
+  if (!grad_rgba || !pixels || !d_pixels || (L > 0 && (!light_positions || !light_intensities)))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(grad_rgba)) return set_error(ctx, PMR_ERR_INVALID, "grad_rgba must be 16-byte aligned");
+  return pmr::shade_diffuse_backward_impl(ctx, grad_rgba, pixels, light_positions, light_intensities, ambient, B, L, A,
+                                          W, H, d_pixels, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -92,4 +92,12 @@ int transform_forward_impl(Context *ctx, const float *matrices, const float *wor
 int transform_backward_impl(Context *ctx, const float *matrices, const float *d_clip, int B, int V, int shared,
                             float *d_world, cudaStream_t stream);
 
+// shade.cu
+int shade_diffuse_forward_impl(Context *ctx, const float *pixels, const float *light_positions,
+                               const float *light_intensities, const float *ambient, int B, int L, int A, int W,
+                               int H, float *rgba, cudaStream_t stream);
+int shade_diffuse_backward_impl(Context *ctx, const float *grad_rgba, const float *pixels,
+                                const float *light_positions, const float *light_intensities, const float *ambient,
+                                int B, int L, int A, int W, int H, float *d_pixels, cudaStream_t stream);
+
 }  // namespace pmr

@@ -161,3 +161,37 @@ def transform_backward(matrices, d_clip, shared):
                                                 _lib.stream_ptr(m.device))
     _lib.check(ctx, rc)
     return out
+
+
+def shade_diffuse_forward(pixels, light_positions, light_intensities, ambient):
+    """pixels [B,H,W,A>=9] -> RGBA [B,H,W,4] (rows flipped), diffuse + ambient Phong terms."""
+    px = _require(pixels, torch.float32, "pixels")
+    lp = _require(light_positions, torch.float32, "light_positions")
+    li = _require(light_intensities, torch.float32, "light_intensities")
+    am = _require(ambient, torch.float32, "ambient_color") if ambient is not None else None
+    B, H, W, A = px.shape
+    rgba = torch.empty((B, H, W, 4), dtype=torch.float32, device=px.device)
+    ctx = _lib.context(px.device.index)
+    with torch.cuda.device(px.device):
+        rc = _lib.load().pmr_shade_diffuse_forward(ctx, _lib.ptr(px), _lib.ptr(lp), _lib.ptr(li), _lib.ptr(am), B,
+                                                   lp.shape[1], A, W, H, _lib.ptr(rgba), _lib.stream_ptr(px.device))
+    _lib.check(ctx, rc)
+    return rgba
+
+
+def shade_diffuse_backward(grad_rgba, pixels, light_positions, light_intensities, ambient):
+    """-> d_pixels [B,H,W,A]."""
+    g = _aligned(_require(grad_rgba, torch.float32, "grad_output"))
+    px = _require(pixels, torch.float32, "pixels")
+    lp = _require(light_positions, torch.float32, "light_positions")
+    li = _require(light_intensities, torch.float32, "light_intensities")
+    am = _require(ambient, torch.float32, "ambient_color") if ambient is not None else None
+    B, H, W, A = px.shape
+    d_pixels = torch.empty_like(px)
+    ctx = _lib.context(px.device.index)
+    with torch.cuda.device(px.device):
+        rc = _lib.load().pmr_shade_diffuse_backward(ctx, _lib.ptr(g), _lib.ptr(px), _lib.ptr(lp), _lib.ptr(li),
+                                                    _lib.ptr(am), B, lp.shape[1], A, W, H, _lib.ptr(d_pixels),
+                                                    _lib.stream_ptr(px.device))
+    _lib.check(ctx, rc)
+    return d_pixels

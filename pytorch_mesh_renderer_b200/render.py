@@ -1,16 +1,48 @@
 """Direct caller of the hot path: `render` / `phong_shader` / `tone_mapper` with the signatures of the
 reference's src/mesh_renderer/render.py (render :16-228, phong_shader :231-386, tone_mapper :389-419),
 device-aware (everything stays on the device of `vertices`; the reference allocates on the CPU, SURVEY
-F11).  Rasterization and attribute interpolation run in the CUDA kernels of libpmr_b200; the Phong
-lighting here is host-side torch code (SURVEY section 8f ranks its fusion into one kernel as the next
-row) and is checked against outputs of the unmodified reference (tests/golden/render_*.npz) and the
-reference's PNG fixtures.
+F11).  Rasterization and attribute interpolation run in the CUDA kernels of libpmr_b200.  The lighting of
+a `render` call without specular colours (diffuse + ambient: the reference's own cube test and BASELINE
+config c1) is ONE kernel forward and one backward (csrc/shade.cu, `shade_diffuse`); the specular branch
+(per-(image, light) normalisation over all pixels, render.py:347-353) and callers that need gradients
+with respect to the lights use the torch-op `phong_shader` below.  Everything is checked against outputs
+of the unmodified reference (tests/golden/render_*.npz) and the reference's PNG fixtures.
 """
 import torch
 import torch.nn.functional as F
 
-from . import camera_utils
+from . import camera_utils, ops
 from .rasterize import rasterize
+
+
+class _ShadeDiffuse(torch.autograd.Function):
+    """normalize(normals) + diffuse/ambient Phong + mask + flip of render.py:201-228 / :231-386 as one
+    kernel each way; differentiable with respect to the pixel attributes."""
+
+    @staticmethod
+    def forward(ctx, pixels, light_positions, light_intensities, ambient_color):
+        rgba = ops.shade_diffuse_forward(pixels, light_positions, light_intensities, ambient_color)
+        ctx.save_for_backward(pixels, light_positions, light_intensities)
+        ctx.ambient = ambient_color
+        return rgba
+
+    @staticmethod
+    def backward(ctx, grad_rgba):
+        pixels, light_positions, light_intensities = ctx.saved_tensors
+        d_pixels = ops.shade_diffuse_backward(grad_rgba.contiguous(), pixels, light_positions, light_intensities,
+                                              ctx.ambient)
+        return d_pixels, None, None, None
+
+
+def shade_diffuse(pixels, light_positions, light_intensities, ambient_color=None):
+    """RGBA [B,H,W,4] (rows flipped like phong_shader's result) from the interpolated attribute image
+    `pixels` [B,H,W,A>=9] = [normal, world position, diffuse colour, ...]; gradients flow to `pixels` only."""
+    return _ShadeDiffuse.apply(pixels.contiguous(), light_positions.contiguous().float(),
+                               light_intensities.contiguous().float(),
+                               ambient_color.contiguous().float() if ambient_color is not None else None)
+
+# lights a fused-kernel call can take (csrc/shade.cu kMaxLights)
+_MAX_FUSED_LIGHTS = 16
 
 
 def _per_image(value, batch, what, device):
@@ -95,6 +127,12 @@ def render(vertices, triangles, normals, diffuse_colors, camera_position, camera
     background = torch.full((vertex_attributes.shape[2],), -1.0, device=device)        # render.py:197
     pixels = rasterize(vertices, vertex_attributes, triangles.to(device), clip_from_world, image_width,
                        image_height, background)
+
+    lights_need_grad = light_positions.requires_grad or light_intensities.requires_grad or (
+        ambient_color is not None and ambient_color.requires_grad)
+    if specular_colors is None and not lights_need_grad and light_positions.shape[1] <= _MAX_FUSED_LIGHTS:
+        image = shade_diffuse(pixels, light_positions, light_intensities, ambient_color)
+        return image.to(home) if home != device else image
 
     pixel_normals = F.normalize(pixels[..., 0:3], p=2, dim=3)
     pixel_positions = pixels[..., 3:6]

@@ -1,0 +1,97 @@
+"""shade_diffuse (csrc/shade.cu): the fused diffuse + ambient Phong kernels against
+
+* the torch-op `phong_shader` mirror of render.py:231-386 (itself checked against outputs of the unmodified
+  reference in test_gpu_render.py) on random attribute images, forward and autograd gradients, and
+* outputs of the unmodified reference's `render` (tests/golden/render_cube_96x72.npz), through `render`.
+
+Lighting is float arithmetic through different libraries, so values are compared within the north-star
+tolerance 1e-6 absolute + 1e-5 relative; gradients additionally relative to their largest magnitude
+(sums of many terms)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pmr():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pytorch_mesh_renderer_b200 as m
+    return m
+
+
+def _random_pixels(B, H, W, A, seed, background_fraction=0.3):
+    g = torch.Generator().manual_seed(seed)
+    px = torch.randn((B, H, W, A), generator=g)
+    px[..., 6:9] = torch.rand((B, H, W, 3), generator=g)                  # diffuse colours in [0, 1)
+    bg = torch.rand((B, H, W), generator=g) < background_fraction
+    px[bg] = -1.0                                                         # what the rasterizer writes there
+    px[0, 0, 0, 0:3] = 0.0                                                # a zero normal (normalize eps path)
+    return px
+
+
+def _mirror(pmr, px, lp, li, ambient):
+    import torch.nn.functional as F
+    from pytorch_mesh_renderer_b200.render import phong_shader
+    normals = F.normalize(px[..., 0:3], p=2, dim=3)
+    mask = (px[..., 6:9] >= 0.0).any(dim=3).to(torch.float32)
+    return phong_shader(normals, mask, px[..., 3:6], lp, li, px[..., 6:9], ambient_color=ambient)
+
+
+@pytest.mark.parametrize("B,H,W,A,L,use_ambient", [(2, 37, 53, 9, 1, False), (3, 16, 40, 9, 3, True),
+                                                  (1, 64, 64, 13, 2, True), (2, 8, 8, 9, 16, False)])
+def test_shade_diffuse_matches_torch_mirror(pmr, B, H, W, A, L, use_ambient):
+    from pytorch_mesh_renderer_b200.render import shade_diffuse
+    g = torch.Generator().manual_seed(100 + L)
+    px = _random_pixels(B, H, W, A, seed=7 + A).cuda()
+    lp = (3.0 * torch.randn((B, L, 3), generator=g)).cuda()
+    li = torch.rand((B, L, 3), generator=g).cuda()
+    ambient = torch.rand((B, 3), generator=g).cuda() if use_ambient else None
+    grad = torch.randn((B, H, W, 4), generator=g).cuda()
+
+    a = px.clone().requires_grad_(True)
+    out = shade_diffuse(a, lp, li, ambient)
+    out.backward(grad)
+    b = px.clone().requires_grad_(True)
+    ref = _mirror(pmr, b, lp, li, ambient)
+    ref.backward(grad)
+
+    o, r = out.detach().cpu().numpy(), ref.detach().cpu().numpy()
+    assert np.array_equal(o[..., 3], r[..., 3])                            # mask identical
+    assert (np.abs(o - r) <= 1e-6 + 1e-5 * np.abs(r)).all(), np.abs(o - r).max()
+    go, gr = a.grad.cpu().numpy(), b.grad.cpu().numpy()
+    assert (go[..., 9:] == 0).all()
+    # the zero-normal pixel: torch's normalize backward divides 0/0 there; compare everything else
+    go[0, 0, 0, 0:3] = gr[0, 0, 0, 0:3] = 0.0
+    err = np.abs(go - gr)
+    assert (err <= 1e-6 + 1e-5 * np.abs(gr) + 2e-6 * np.abs(gr).max()).all(), (err.max(), np.abs(gr).max())
+
+
+def test_render_uses_the_fused_shader_and_matches_reference(pmr):
+    """render() without specular goes through shade_diffuse; same goldens as test_gpu_render.py."""
+    from pytorch_mesh_renderer_b200 import _lib
+    c = load_golden("render_cube_96x72")
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    v = dev(c["vertices"]).requires_grad_(True)
+    n = dev(c["normals"]).requires_grad_(True)
+    d = dev(c["diffuse"]).requires_grad_(True)
+    index = torch.cuda.current_device()
+    _lib.enable_stage_timing(index, True)
+    _lib.read_stage_timing(index, reset=True)
+    with pmr.backward_mode("ordered"):
+        out = pmr.render(v, dev(c["triangles"]), n, d, dev(c["eye"]), dev(c["center"]), dev(c["up"]),
+                         dev(c["light_positions"]), dev(c["light_intensities"]), int(c["width"]), int(c["height"]))
+        out.backward(dev(c["grad_out"]))
+    stages = _lib.read_stage_timing(index, reset=True)
+    _lib.enable_stage_timing(index, False)
+    assert stages["shade"][1] == 2                                         # one forward, one backward launch
+    img = out.detach().cpu().numpy()
+    assert np.array_equal(img[..., 3], c["image"][..., 3])
+    assert (np.abs(img - c["image"]) <= 1e-5 + 1e-4 * np.abs(c["image"])).all()
+    for mine, key in ((v.grad, "d_vertices"), (n.grad, "d_normals"), (d.grad, "d_diffuse")):
+        ref = c[key]
+        assert np.abs(mine.cpu().numpy() - ref).max() <= 2e-4 * (np.abs(ref).max() + 1e-12), key
