@@ -39,24 +39,23 @@ __device__ __forceinline__ void load_lights(Lights &sm, const float *__restrict_
   __syncthreads();
 }
 
-// v / max(|v|, eps) (render.py:201 and :318-321); returns the length.
-__device__ __forceinline__ float normalize3(const float v[3], float out[3]) {
-  const float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-  const float denom = fmaxf(len, kNormalizeEps);
-  out[0] = v[0] / denom; out[1] = v[1] / denom; out[2] = v[2] / denom;
-  return len;
+// v / max(|v|, eps) (render.py:201 and :318-321) as one IEEE reciprocal and three multiplies (within
+// 1.5 ulp of the three divisions torch performs).  Returns 1 / max(|v|, eps); `len` receives |v|.
+__device__ __forceinline__ float normalize3(const float v[3], float out[3], float &len) {
+  len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  const float inv = 1.0f / fmaxf(len, kNormalizeEps);
+  out[0] = v[0] * inv; out[1] = v[1] * inv; out[2] = v[2] * inv;
+  return inv;
 }
 
 // Backward of normalize3: g = d(loss)/d(out) -> d(loss)/d(v).  torch: v / norm.clamp_min(eps); the
-// clamp passes gradient to the norm when norm >= eps, and the norm's own gradient is v / norm (0 at 0).
-__device__ __forceinline__ void normalize3_backward(const float v[3], const float unit[3], float len,
+// clamp passes gradient to the norm when norm >= eps (then v / norm is `unit` itself), and not below.
+__device__ __forceinline__ void normalize3_backward(const float unit[3], float len, float inv,
                                                     const float g[3], float dv[3]) {
-  const float denom = fmaxf(len, kNormalizeEps);
   const float dot = g[0] * unit[0] + g[1] * unit[1] + g[2] * unit[2];      // = sum(g * v) / denom
-  const float through_norm = (len >= kNormalizeEps && len > 0.0f) ? dot / denom : 0.0f;
+  const float through_norm = len >= kNormalizeEps ? dot * inv : 0.0f;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) dv[k] = g[k] / denom - through_norm * (v[k] / len);
-  (void)v;
+  for (int k = 0; k < 3; ++k) dv[k] = g[k] * inv - through_norm * unit[k];
 }
 
 // One thread per pixel.  pixels [B,H,W,A] (channels 0..8 used), rgba [B,H,W,4] with rows flipped
@@ -75,13 +74,13 @@ shade_diffuse_forward_kernel(const float *__restrict__ pixels, const float *__re
   const float n_raw[3] = {px[0], px[1], px[2]}, pos[3] = {px[3], px[4], px[5]}, kd[3] = {px[6], px[7], px[8]};
   // background pixels carry diffuse = -1 in every channel (render.py:197, :215)
   const float alpha = (kd[0] >= 0.0f || kd[1] >= 0.0f || kd[2] >= 0.0f) ? 1.0f : 0.0f;
-  float n[3];
-  normalize3(n_raw, n);
+  float n[3], len;
+  normalize3(n_raw, n, len);
   float rgb[3] = {0.0f, 0.0f, 0.0f};
   for (int l = 0; l < L; ++l) {
     const float d[3] = {sm.pos[l][0] - pos[0], sm.pos[l][1] - pos[1], sm.pos[l][2] - pos[2]};
     float u[3];
-    normalize3(d, u);
+    normalize3(d, u, len);
     const float ndl = fminf(fmaxf(n[0] * u[0] + n[1] * u[1] + n[2] * u[2], 0.0f), 1.0f);
 #pragma unroll
     for (int c = 0; c < 3; ++c) rgb[c] += kd[c] * ndl * sm.intensity[l][c];
@@ -103,26 +102,27 @@ shade_diffuse_backward_kernel(const float4 *__restrict__ grad_rgba, const float 
                               const float *__restrict__ ambient, int L, int A, int W, int H,
                               float *__restrict__ d_pixels) {
   __shared__ Lights sm;
+  extern __shared__ float stage[];          // [256][A]: the CTA's pixels are contiguous in d_pixels
   const int b = blockIdx.y;
   load_lights(sm, light_positions, light_intensities, ambient, b, L);
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= W * H) return;
-  const int y = p / W, x = p - y * W;
-  const float *px = pixels + ((size_t)b * H * W + p) * A;
-  float *out = d_pixels + ((size_t)b * H * W + p) * A;
+  const int p0 = blockIdx.x * blockDim.x, p = p0 + threadIdx.x;
+  const bool in_image = p < W * H;
+  const int y = in_image ? p / W : 0, x = in_image ? p - y * W : 0;
+  const float *px = pixels + ((size_t)b * H * W + (in_image ? p : 0)) * A;
+  float *out = stage + threadIdx.x * A;
   const float n_raw[3] = {px[0], px[1], px[2]}, pos[3] = {px[3], px[4], px[5]}, kd[3] = {px[6], px[7], px[8]};
   float d_n[3] = {0.0f, 0.0f, 0.0f}, d_pos[3] = {0.0f, 0.0f, 0.0f}, d_kd[3] = {0.0f, 0.0f, 0.0f};
-  const bool valid = kd[0] >= 0.0f || kd[1] >= 0.0f || kd[2] >= 0.0f;
+  const bool valid = in_image && (kd[0] >= 0.0f || kd[1] >= 0.0f || kd[2] >= 0.0f);
   if (valid) {
     const float4 g4 = grad_rgba[((size_t)b * H + (H - 1 - y)) * W + x];
     const float g[3] = {g4.x, g4.y, g4.z};                 // alpha comes from a comparison: no gradient
-    float n[3];
-    const float n_len = normalize3(n_raw, n);
+    float n[3], n_len;
+    const float n_inv = normalize3(n_raw, n, n_len);
     float d_unit_n[3] = {0.0f, 0.0f, 0.0f};
     for (int l = 0; l < L; ++l) {
       const float d[3] = {sm.pos[l][0] - pos[0], sm.pos[l][1] - pos[1], sm.pos[l][2] - pos[2]};
-      float u[3];
-      const float d_len = normalize3(d, u);
+      float u[3], d_len;
+      const float d_inv = normalize3(d, u, d_len);
       const float s = n[0] * u[0] + n[1] * u[1] + n[2] * u[2];
       const float ndl = fminf(fmaxf(s, 0.0f), 1.0f);
       float d_ndl = 0.0f;
@@ -134,7 +134,7 @@ shade_diffuse_backward_kernel(const float4 *__restrict__ grad_rgba, const float 
       const float d_s = (s >= 0.0f && s <= 1.0f) ? d_ndl : 0.0f;        // torch.clamp passes on the closed interval
       const float d_u[3] = {d_s * n[0], d_s * n[1], d_s * n[2]};
       float d_d[3];
-      normalize3_backward(d, u, d_len, d_u, d_d);
+      normalize3_backward(u, d_len, d_inv, d_u, d_d);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         d_unit_n[k] += d_s * u[k];
@@ -145,11 +145,17 @@ shade_diffuse_backward_kernel(const float4 *__restrict__ grad_rgba, const float 
 #pragma unroll
       for (int c = 0; c < 3; ++c) d_kd[c] += g[c] * sm.ambient[c];
     }
-    normalize3_backward(n_raw, n, n_len, d_unit_n, d_n);
+    normalize3_backward(n, n_len, n_inv, d_unit_n, d_n);
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) { out[k] = d_n[k]; out[3 + k] = d_pos[k]; out[6 + k] = d_kd[k]; }
   for (int k = 9; k < A; ++k) out[k] = 0.0f;
+  __syncthreads();
+  // coalesced write-back of the CTA's contiguous run of pixels (A is odd or even: staging rows of A floats
+  // are read linearly, so there are no bank conflicts here; the writes above conflict only for even A)
+  const int n_pixels = min((int)blockDim.x, W * H - p0);
+  float *dst = d_pixels + ((size_t)b * H * W + p0) * A;
+  for (int i = threadIdx.x; i < n_pixels * A; i += blockDim.x) dst[i] = stage[i];
 }
 
 int shade_diffuse_forward_impl(Context *ctx, const float *pixels, const float *light_positions,
@@ -170,7 +176,9 @@ int shade_diffuse_backward_impl(Context *ctx, const float *grad_rgba, const floa
   if (B == 0) return PMR_OK;
   if (L > kMaxLights) return set_error(ctx, PMR_ERR_SIZE, "at most %d lights", kMaxLights);
   StageScope timed(ctx, PMR_STAGE_SHADE, stream);
-  shade_diffuse_backward_kernel<<<dim3((unsigned)(((long long)W * H + 255) / 256), B), 256, 0, stream>>>(
+  const size_t smem = (size_t)256 * A * sizeof(float);
+  if (smem > 40 * 1024) return set_error(ctx, PMR_ERR_SIZE, "at most 40 pixel channels");
+  shade_diffuse_backward_kernel<<<dim3((unsigned)(((long long)W * H + 255) / 256), B), 256, smem, stream>>>(
       reinterpret_cast<const float4 *>(grad_rgba), pixels, light_positions, light_intensities, ambient, L, A, W, H,
       d_pixels);
   ctx->launches += 1;
