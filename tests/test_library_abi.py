@@ -59,3 +59,15 @@ def test_argument_errors_keep_reference_types():
         m.rasterize_clip_space(v, a, t, 0, 4, torch.zeros(2))
     with pytest.raises(ValueError, match="must be 3D"):
         m.rasterize_clip_space(v[0], a, t, 4, 4, torch.zeros(2))
+
+
+def test_both_build_recipes_compile_every_source():
+    """build.py (what __graft_entry__.build() runs) and csrc/Makefile list the same .cu files: all of them."""
+    import glob
+    from pytorch_mesh_renderer_b200 import build
+    csrc = os.path.join(ROOT, "pytorch_mesh_renderer_b200", "csrc")
+    on_disk = sorted(os.path.basename(p) for p in glob.glob(os.path.join(csrc, "*.cu")))
+    assert sorted(build.SOURCES) == on_disk
+    makefile = open(os.path.join(csrc, "Makefile")).read()
+    listed = re.search(r"^SRCS\s*:=\s*(.*)$", makefile, re.M).group(1).split()
+    assert sorted(listed) == on_disk
