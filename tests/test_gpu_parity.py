@@ -314,3 +314,47 @@ def assert_close_t(a, b, tol):
     a, b = a.detach().float().cpu().numpy(), b.detach().float().cpu().numpy()
     scale = np.abs(b).max() + 1e-30
     assert np.abs(a - b).max() <= tol * scale, (np.abs(a - b).max(), scale)
+
+
+def _large_triangle_soup(rng, n, spread=1.2):
+    """n triangles with vertices spread over (and beyond) the screen: pixel boxes far above 16x16."""
+    xy = rng.uniform(-spread, spread, (n, 3, 2))
+    z = rng.uniform(-0.9, 0.9, (n, 3, 1))
+    w = rng.uniform(0.5, 2.0, (n, 3, 1))
+    v = np.concatenate([xy, z, np.ones_like(z)], 2) * w
+    return v.reshape(-1, 4).astype(np.float32), np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+
+
+def test_tile_kernel_many_candidates_per_macro_tile(pmr, oracle):
+    """3 000 screen-sized triangles on one 96x80 image: every 64x64 macro tile sees more than the 1 024
+    candidates its shared-memory list holds, so the tile kernel works in several passes that merge through
+    the global depth keys (raster_tile_kernel, kMacroCap)."""
+    from pytorch_mesh_renderer_b200 import ops
+    v, t = _large_triangle_soup(np.random.default_rng(11), 3000)
+    ids, bary, z = ops.rasterize_forward(dev(v)[None], dev(t), 96, 80)
+    ref_ids, ref_bary, ref_z = oracle.forward(v, t, 96, 80)
+    assert_bits(ids[0].cpu().numpy(), ref_ids, "ids")
+    assert_bits(bary[0].cpu().numpy(), ref_bary, "bary")
+    assert_bits(z[0].cpu().numpy(), ref_z, "z")
+
+
+def test_tile_kernel_more_images_than_one_slice(pmr, oracle):
+    """300 small images (the tile kernel lists the images with large triangles in slices of 256), a third of
+    them without any triangle that reaches the tile path."""
+    from pytorch_mesh_renderer_b200 import ops
+    rng = np.random.default_rng(12)
+    B, W, H, n = 300, 40, 24, 70
+    vs = []
+    for b in range(B):
+        v, t = _large_triangle_soup(rng, n)
+        if b % 3 == 1:
+            v[:, :2] *= 0.05                      # only small triangles in this image
+        vs.append(v)
+    v = np.stack(vs)
+    ids, bary, z = ops.rasterize_forward(dev(v), dev(t), W, H)
+    ids, bary, z = ids.cpu().numpy(), bary.cpu().numpy(), z.cpu().numpy()
+    for b in range(0, B, 7):
+        ref_ids, ref_bary, ref_z = oracle.forward(v[b], t, W, H)
+        assert_bits(ids[b], ref_ids, "ids of image %d" % b)
+        assert_bits(bary[b], ref_bary, "bary of image %d" % b)
+        assert_bits(z[b], ref_z, "z of image %d" % b)
