@@ -40,6 +40,15 @@ WORKLOADS = {
 }
 
 
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle on it and point fd 1 at stderr, so that
+    whatever libraries print there (NCCL's version banner under torchrun, for one) cannot precede the line."""
+    out = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return out
+
+
 def make_workload(name, batch_override=None):
     from pytorch_mesh_renderer_b200 import synthetic as S
     if name == "c1":
@@ -67,7 +76,7 @@ class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU while the timed region runs, in a separate
     nvidia-smi process (the recipe's clocks line) so that the Python launch loop cannot starve it."""
 
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
@@ -84,31 +93,51 @@ class ClockSampler:
             self.proc = None
 
     def start(self):
-        time.sleep(0.05)          # let the first samples arrive before the timed region begins
+        """Blocks until the first sample has arrived (nvidia-smi takes a while to come up), then marks the
+        beginning of the timed region."""
+        import select
+        self.head = ""
+        if self.proc is not None:
+            ready, _, _ = select.select([self.proc.stdout], [], [], 3.0)
+            if ready:
+                self.head = self.proc.stdout.readline()
+        self.t_begin = time.time()
 
     def stop(self):
-        samples, reasons, max_mhz = [], set(), None
+        import datetime
+        self.t_end = time.time()
+        samples, reasons, max_mhz, nearby = [], set(), None, []
         if self.proc is not None:
-            time.sleep(0.02)
+            time.sleep(0.03)
             self.proc.terminate()
             try:
                 out, _ = self.proc.communicate(timeout=5)
             except Exception:
                 out = ""
-            for line in out.splitlines():
+            for line in (self.head + out).splitlines():
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 6:
+                if len(f) < 7:
                     continue
                 try:
-                    samples.append(float(f[0]))
-                    max_mhz = float(f[1])
+                    stamp = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    mhz = float(f[1])
+                    max_mhz = float(f[2])
                 except ValueError:
                     continue
-                for name, v in zip(self.NAMES, f[2:6]):
+                inside = self.t_begin - 0.005 <= stamp <= self.t_end + 0.005
+                if not inside:
+                    if abs(stamp - self.t_begin) < 0.25 or abs(stamp - self.t_end) < 0.25:
+                        nearby.append(mhz)
+                    continue
+                samples.append(mhz)
+                for name, v in zip(self.NAMES, f[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
+        window = "timed region"
+        if not samples and nearby:          # region shorter than the sampling period: nearest samples
+            samples, window = nearby, "within 250 ms of the timed region"
         return {"sm_mhz": statistics.median(samples) if samples else None, "sm_max_mhz": max_mhz,
-                "reasons": sorted(reasons), "samples": len(samples)}
+                "reasons": sorted(reasons), "samples": len(samples), "window": window}
 
 
 def run_reference(args, rank):
@@ -139,7 +168,8 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    args.out.write(json.dumps(line) + "\n")
+    args.out.flush()
 
 
 def main():
@@ -155,6 +185,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.out = claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,8 +217,6 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     sc = make_workload(args.config, args.batch)
@@ -233,10 +262,11 @@ def main():
         for _ in range(args.warmup):
             step()
         torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank if rank == 0 else None)   # one sampler per job, not per rank
+        sampler.start()                                              # returns once samples are flowing
         if world > 1:
             dist.barrier()
-        sampler = ClockSampler(local_rank if rank == 0 else None)   # one sampler per job, not per rank
-        sampler.start()
+        sampler.t_begin = time.time()
         _lib.enable_stage_timing(local_rank, True)
         _lib.read_stage_timing(local_rank, reset=True)
         launches0 = _lib.launch_count(local_rank)
@@ -360,7 +390,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        args.out.write(json.dumps(line) + "\n")
+        args.out.flush()
     if world > 1:
         dist.destroy_process_group()
 
