@@ -242,6 +242,52 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
     store_block_rows<(A_STATIC > 0 ? A_STATIC : 1)>(stage + kImageAt, out_image + p0 * A, W * A, cols, rows, vec_ok);
 }
 
+// Conservative lower bound of the depth any pixel centre in the rectangle [px0,px1] x [py0,py1] can get
+// from one triangle (all w > 0), or -inf when no bound can be given.  Hierarchical z at block granularity:
+// the triangle-level bound (min of the vertex depths) is useless for a large slanted triangle that is far
+// behind the surface in THIS block.
+//
+// Why it is conservative.  The reference's depth at a pixel (K.cpp:384-397) is, up to roundings,
+//   Z(e) = sum_i e_i z_i / sum_i e_i w_i  with the COMPUTED edge values e_i >= 0 as weights.
+// With E_i(p) = a_i px + b_i py + c_i the exact edge functions of the fp32 coefficients, N(p) = sum z_i E_i(p)
+// and D(p) = sum w_i E_i(p) are affine in p, so R = N / D is quasi-linear wherever D > 0: over the rectangle
+// its minimum sits at a corner.  Error terms, with eps = 2^-24, mag_i >= |a_i px| + |b_i py| + |c_i| on the
+// rectangle, Ed = sum w_i mag_i, dabs = max |z_i / w_i|, q = 16 eps Ed / Dmin:
+//   |e_i - E_i(p)| <= 4 eps mag_i  ==>  Z(e) >= R(p) - (q/3) S,  S = spread of {z_i / w_i} and R   (weights lemma:
+//                                       Z(e) - R(p) = sum_i (e_i - E_i) w_i (z_i/w_i - R) / sum_i e_i w_i)
+//   corner values computed from the affine coefficients in fp32:  |R~(c) - R(c)| <= q (dabs + |R~|)
+//   roundings of K.cpp:384-397 (three divisions, two dot products, one division): <= 10 eps dabs
+//   the approximate divisions used here: 2^-21 relative.
+// Everything is charged twice below, and the bound is only used when q <= 1/64 and D > 0 at all four corners
+// (then D > 0 on the whole rectangle even with its own evaluation error).
+__device__ __forceinline__ float block_depth_bound(const float ea[3], const float eb[3], const float ec[3],
+                                                   const float mag[3], const float zc[3], const float wc[3],
+                                                   float px0, float px1, float py0, float py1) {
+  const float an = __fmaf_rn(zc[2], ea[2], __fmaf_rn(zc[1], ea[1], zc[0] * ea[0]));
+  const float bn = __fmaf_rn(zc[2], eb[2], __fmaf_rn(zc[1], eb[1], zc[0] * eb[0]));
+  const float cn = __fmaf_rn(zc[2], ec[2], __fmaf_rn(zc[1], ec[1], zc[0] * ec[0]));
+  const float ad = __fmaf_rn(wc[2], ea[2], __fmaf_rn(wc[1], ea[1], wc[0] * ea[0]));
+  const float bd = __fmaf_rn(wc[2], eb[2], __fmaf_rn(wc[1], eb[1], wc[0] * eb[0]));
+  const float cd = __fmaf_rn(wc[2], ec[2], __fmaf_rn(wc[1], ec[1], wc[0] * ec[0]));
+  const float ny0 = __fmaf_rn(bn, py0, cn), ny1 = __fmaf_rn(bn, py1, cn);
+  const float dy0 = __fmaf_rn(bd, py0, cd), dy1 = __fmaf_rn(bd, py1, cd);
+  const float n00 = __fmaf_rn(an, px0, ny0), n10 = __fmaf_rn(an, px1, ny0), n01 = __fmaf_rn(an, px0, ny1), n11 = __fmaf_rn(an, px1, ny1);
+  const float d00 = __fmaf_rn(ad, px0, dy0), d10 = __fmaf_rn(ad, px1, dy0), d01 = __fmaf_rn(ad, px0, dy1), d11 = __fmaf_rn(ad, px1, dy1);
+  const float dmin = fminf(fminf(d00, d10), fminf(d01, d11));
+  const float ed = __fmaf_rn(wc[2], mag[2], __fmaf_rn(wc[1], mag[1], wc[0] * mag[0]));
+  // q = 16 eps Ed / Dmin <= 1/64  <=>  Ed * 2^-14 <= Dmin   (also rejects Dmin <= 0 and NaN)
+  if (!(ed * 6.1035156e-5f <= dmin)) return -INFINITY;
+  const float q = __fdividef(ed * 9.5367432e-7f, dmin);
+  const float r00 = __fdividef(n00, d00), r10 = __fdividef(n10, d10), r01 = __fdividef(n01, d01), r11 = __fdividef(n11, d11);
+  const float rlow = fminf(fminf(r00, r10), fminf(r01, r11));
+  const float rabs = fmaxf(fmaxf(fabsf(r00), fabsf(r10)), fmaxf(fabsf(r01), fabsf(r11)));
+  const float dabs = fmaxf(fmaxf(fabsf(__fdividef(zc[0], wc[0])), fabsf(__fdividef(zc[1], wc[1]))),
+                           fabsf(__fdividef(zc[2], wc[2])));
+  const float scale = (dabs + rabs) * 1.0001f;
+  // S <= 2 (dabs + rabs):  2 * [ (q/3) S + q (dabs + rabs) ] <= 4 q scale;  roundings: 2^-19 scale
+  return rlow - scale * (4.0f * q + 1.9073486e-6f) - 1e-30f;
+}
+
 // Packed pixel box vs the pixel rectangle [x0, x0 + w) x [y0, y0 + h).
 __device__ __forceinline__ bool box_touches_rect(uint2 packed, int x0, int y0, int w, int h) {
   const int4 bx = unpack_box(packed);
@@ -265,11 +311,11 @@ constexpr int kTinyMeshMax = kMacroCap;      // largest mesh the tiny-mesh mode 
 //                            (keys_out == nullptr);
 //   large_count != nullptr   pipeline mode: image b has large_count[b] large triangles, ids and packed
 //                            boxes in large_ids / large_boxes[b * T ...]; the result is merged into keys_out.
-template <int A_STATIC>
+template <int A_STATIC, bool PIPELINE>
 __global__ void __launch_bounds__(kChunk, 4)
 raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris,
                    int B, int V, int T, int W, int H, float half_w, float half_h, int tiles_x, int tiles_y,
-                   int macro_tiles, int *__restrict__ work_cursor, const int *__restrict__ large_count, const int32_t *__restrict__ large_ids,
+                   int macro_shift, int *__restrict__ work_cursor, const int *__restrict__ large_count, const int32_t *__restrict__ large_ids,
                    const uint2 *__restrict__ large_boxes,
                    int32_t *__restrict__ out_ids, float *__restrict__ out_bary, float *__restrict__ out_z,
                    const float *__restrict__ attrs, const float *__restrict__ background, int A_dyn,
@@ -278,7 +324,8 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
   const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lanes_below = (1u << lane) - 1u;
-  const int macros_x = (tiles_x + macro_tiles - 1) / macro_tiles, macros_y = (tiles_y + macro_tiles - 1) / macro_tiles;
+  const int macro_tiles = 1 << macro_shift;               // 1, 2 or 4 screen tiles on a side
+  const int macros_x = (tiles_x + macro_tiles - 1) >> macro_shift, macros_y = (tiles_y + macro_tiles - 1) >> macro_shift;
   const int macros_per_image = macros_x * macros_y;
   // Work items are handed out through a global counter (item costs differ by an order of magnitude
   // between busy and empty screen regions); `grabbed` only ever grows, the slices consume it in order.
@@ -290,7 +337,8 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
   };
   int grabbed = grab_item();
   int slice_begin = 0;
-  const bool pipeline = large_count != nullptr;
+  constexpr bool pipeline = PIPELINE;                     // compile-time: the tiny-mesh epilogue and the
+                                                          // barycentrics of the running winner drop out
   // 8 warps, each an 8x4 pixel block; blocks are laid out 2 across, 4 down inside the 16x16 tile.
   const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
 
@@ -349,7 +397,7 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
     if (n_macro == 0 && pipeline) continue;                // nothing of this range reaches the macro tile
 
   for (int sub = 0; sub < macro_tiles * macro_tiles; ++sub) {
-    const int tile_tx = macro_tx * macro_tiles + (sub & (macro_tiles - 1)), tile_ty = macro_ty * macro_tiles + sub / macro_tiles;
+    const int tile_tx = macro_tx * macro_tiles + (sub & (macro_tiles - 1)), tile_ty = macro_ty * macro_tiles + (sub >> macro_shift);
     if (tile_tx >= tiles_x || tile_ty >= tiles_y) continue;
     const int tile_x0 = tile_tx * kTileW, tile_y0 = tile_ty * kTileH;
     const int blk_x0 = tile_x0 + (warp & 1) * 8, blk_y0 = tile_y0 + (warp >> 1) * 4;
@@ -370,7 +418,8 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
     const float blk_px0 = sm.cx[(warp & 1) * 8], blk_px1 = sm.cx[(warp & 1) * 8 + 7];
     const float blk_py0 = sm.cy[(warp >> 1) * 4], blk_py1 = sm.cy[(warp >> 1) * 4 + 3];
     const float blk_pxabs = fmaxf(fabsf(blk_px0), fabsf(blk_px1)), blk_pyabs = fmaxf(fabsf(blk_py0), fabsf(blk_py1));
-    if (keys_out != nullptr && ix < W && iy < H) {
+    const float tile_pxabs = fmaxf(fabsf(sm.cx[0]), fabsf(sm.cx[kTileW - 1])), tile_pyabs = fmaxf(fabsf(sm.cy[0]), fabsf(sm.cy[kTileH - 1]));
+    if (PIPELINE && ix < W && iy < H) {
       // pipeline mode: start from what is already drawn (small triangles, earlier passes); depth and id
       // are all the depth rule needs, barycentrics are not produced in this mode
       const unsigned long long seen = keys_out[((size_t)b * H + iy) * W + ix];
@@ -439,15 +488,29 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
           const float dabs = fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fabsf(d2));
           zlo = fminf(fminf(d0, d1), d2) - dabs * 1.9073486e-6f - 1e-30f;
         }
-        sm.zlo[threadIdx.x] = zlo;
         // the box inside this tile, in tile-local pixel coordinates
         x0 = max(bx.x, tile_x0) - tile_x0; x1 = min(bx.y, tile_x0 + kTileW) - tile_x0;
         y0 = max(bx.z, tile_y0) - tile_y0; y1 = min(bx.w, tile_y0 + kTileH) - tile_y0;
         overlaps = x1 > x0 && y1 > y0;
+        if (overlaps && zlo > -INFINITY) {
+          // Tighten the bound to THIS tile (block_depth_bound over the tile's pixel centres): a large slanted
+          // triangle is then sorted, and culled, by where it is here, not by its nearest vertex.
+          const float ea[3] = {m[0], m[3], m[6]}, eb[3] = {m[1], m[4], m[7]}, ec[3] = {m[2], m[5], m[8]};
+          const float zc[3] = {p0.z, p1.z, p2.z}, wc[3] = {p0.w, p1.w, p2.w};
+          float mag[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) mag[i] = fabsf(ea[i]) * tile_pxabs + fabsf(eb[i]) * tile_pyabs + fabsf(ec[i]);
+          zlo = fmaxf(zlo, block_depth_bound(ea, eb, ec, mag, zc, wc, sm.cx[0], sm.cx[kTileW - 1], sm.cy[0], sm.cy[kTileH - 1]));
+        }
+        sm.zlo[threadIdx.x] = zlo;
         if (overlaps && (x1 - x0) * (y1 - y0) <= 64) n_seg = (y1 - y0) * ((x1 - x0 + 3) >> 2);
       }
       // ---- the warp lays the row segments of ITS small triangles out back to back (warp scan).
       // Triangles whose segments do not fit the warp's buffer, and all large ones, take the big path.
+      // The segment path pays when a good part of the warp has such triangles (a mesh of small triangles);
+      // a few stragglers (corners of large triangles clipped by the tile) would run its loops with one
+      // or two lanes active, so they take the big path, which draws anything.
+      if (__popc(__ballot_sync(0xffffffffu, n_seg > 0)) < 8) n_seg = 0;
       const int seg_end = warp_inclusive_scan(n_seg);
       const bool small = n_seg > 0 && seg_end <= kWarpSegCap;
       unsigned *segs = sm.segs[warp];
@@ -553,11 +616,18 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
             // no pixel of the block can pass the inside test (K.cpp:93-98).
             const float4 q0 = sm.r0[jj], q1 = sm.r1[jj], q2 = sm.r2[jj];
             const float ea[3] = {q0.x, q1.x, q2.x}, eb[3] = {q0.y, q1.y, q2.y}, ec[3] = {q0.z, q1.z, q2.z};
+            float mag[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
               const float hi = ea[i] * (ea[i] >= 0.0f ? blk_px1 : blk_px0) + eb[i] * (eb[i] >= 0.0f ? blk_py1 : blk_py0) + ec[i];
-              const float mag = fabsf(ea[i]) * blk_pxabs + fabsf(eb[i]) * blk_pyabs + fabsf(ec[i]);
-              if (hi < -9.5367432e-7f * mag) touches = false;             // 2^-20 = 16 ulp of the magnitude sum
+              mag[i] = fabsf(ea[i]) * blk_pxabs + fabsf(eb[i]) * blk_pyabs + fabsf(ec[i]);
+              if (hi < -9.5367432e-7f * mag[i]) touches = false;          // 2^-20 = 16 ulp of the magnitude sum
+            }
+            if (touches && sm.zlo[jj] > -INFINITY) {                      // all w > 0 (see the staging code)
+              const float4 q3 = sm.r3[jj];
+              const float zc[3] = {q1.w, q2.w, q3.x}, wc[3] = {q3.y, q3.z, q3.w};
+              if (block_depth_bound(ea, eb, ec, mag, zc, wc, blk_px0, blk_px1, blk_py0, blk_py1) > block_zmax)
+                touches = false;
             }
           }
         }
@@ -591,7 +661,7 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
     // ---- resolve: minimum of the two paths (all keys final; record planes dead from here on)
     const unsigned long long key_small = sm.key[ly * kTileW + lx];
     const unsigned long long key_big = best.id >= 0 ? depth_key(best.z, best.id) : kEmptyKey;
-    if (keys_out != nullptr) {
+    if constexpr (PIPELINE) {
       // large-triangle pass of the pipeline: merge into the global keys (this CTA is the only
       // writer of its pixels now; the scatter kernel has finished), resolve_kernel does the rest.
       if (ix < W && iy < H) {
@@ -599,17 +669,17 @@ raster_tile_kernel(const float *__restrict__ verts, const int32_t *__restrict__ 
         const unsigned long long mine = min(key_small, key_big);
         if (mine < keys_out[p]) keys_out[p] = mine;
       }
-      continue;
+    } else {
+      if (key_small < key_big) {     // the winner came through the key buffer: re-evaluate it once
+        const int t = depth_key_id(key_small);
+        float4 p0, p1, p2;
+        load_triangle(verts_b, tris, t, p0, p1, p2);
+        evaluate_winner(p0, p1, p2, px, py, t, best);
+      }
+      float *stage = reinterpret_cast<float *>(sm.r0) + warp * (32 * 16);
+      block_epilogue<A_STATIC>(stage, b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
+                               out_ids, out_bary, out_z, out_image);
     }
-    if (key_small < key_big) {     // the winner came through the key buffer: re-evaluate it once
-      const int t = depth_key_id(key_small);
-      float4 p0, p1, p2;
-      load_triangle(verts_b, tris, t, p0, p1, p2);
-      evaluate_winner(p0, p1, p2, px, py, t, best);
-    }
-    float *stage = reinterpret_cast<float *>(sm.r0) + warp * (32 * 16);
-    block_epilogue<A_STATIC>(stage, b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
-                             out_ids, out_bary, out_z, out_image);
   }                          // tiles of the macro tile
   } while (next < n_cand);   // passes over the image's candidates
   }                          // work items
@@ -854,26 +924,29 @@ static int launch_raster(Context *ctx, const float *verts, const int32_t *tris, 
   // persistent CTAs: 4 per SM (launch bounds), fewer when there is less work than that.  Macro tiles of
   // 4x4 screen tiles amortise the candidate scan 16-fold; small jobs use smaller ones to keep every SM busy.
   const long long resident = (long long)ctx->sm_count * 4;
-  int macro_tiles = kMacroTiles;
+  static_assert(kMacroTiles == 4, "macro_shift below starts at log2(kMacroTiles)");
+  int macro_shift = 2;
   long long n_items = 0;
-  for (;; macro_tiles >>= 1) {
+  for (;; --macro_shift) {
+    const int macro_tiles = 1 << macro_shift;
     n_items = (long long)B * ((tiles_x + macro_tiles - 1) / macro_tiles) * ((tiles_y + macro_tiles - 1) / macro_tiles);
-    if (macro_tiles == 1 || n_items >= 4 * resident) break;
+    if (macro_shift == 0 || n_items >= 4 * resident) break;
   }
   if (n_items > (long long)INT_MAX / 2) return set_error(ctx, PMR_ERR_SIZE, "too many screen tiles");
   const int grid = (int)(n_items < resident ? n_items : resident);
   StageScope timed(ctx, PMR_STAGE_RASTER, stream);
-#define PMR_LAUNCH(AS)                                                                              \
-  raster_tile_kernel<AS><<<grid, kChunk, 0, stream>>>(verts, tris, B, V, T, W, H, half_w, half_h,   \
-                                                     tiles_x, tiles_y, macro_tiles, work_cursor,    \
+#define PMR_LAUNCH(AS, PIPE)                                                                        \
+  raster_tile_kernel<AS, PIPE><<<grid, kChunk, 0, stream>>>(verts, tris, B, V, T, W, H, half_w, half_h, \
+                                                     tiles_x, tiles_y, macro_shift, work_cursor,    \
                                                      large_count, large_ids,                        \
                                                      large_boxes, ids, bary, z, attrs, bg, A, image, keys_out)
-  if (image == nullptr || keys_out != nullptr) PMR_LAUNCH(0);
-  else if (A == 4) PMR_LAUNCH(4);
-  else if (A == 9) PMR_LAUNCH(9);
-  else if (A == 12) PMR_LAUNCH(12);
-  else if (A == 13) PMR_LAUNCH(13);
-  else PMR_LAUNCH(0);
+  if (keys_out != nullptr) PMR_LAUNCH(0, true);
+  else if (image == nullptr) PMR_LAUNCH(0, false);
+  else if (A == 4) PMR_LAUNCH(4, false);
+  else if (A == 9) PMR_LAUNCH(9, false);
+  else if (A == 12) PMR_LAUNCH(12, false);
+  else if (A == 13) PMR_LAUNCH(13, false);
+  else PMR_LAUNCH(0, false);
 #undef PMR_LAUNCH
   ctx->launches += 1;
   return check_launch(ctx, "raster_tile_kernel");
