@@ -58,10 +58,13 @@ def atomic_close(actual, ref32, ref64, what):
     """ATOMIC mode sums the same fp32 terms in another order: its distance from the exactly summed
     value must be of the order of the reference's own distance from it (oracle.atomic_mode_bound)."""
     from oracle import oracle as o
-    err = np.abs(np.asarray(actual, np.float64) - ref64)
-    bound = o.atomic_mode_bound(ref32, ref64)
+    actual = np.asarray(actual, np.float64)
+    finite = np.isfinite(ref64) & np.isfinite(np.asarray(ref32, np.float64))
+    assert (np.isfinite(actual) == finite).all(), "%s: non-finite entries differ from the reference's" % what
+    err = np.abs(actual - ref64)[finite]
+    bound = o.atomic_mode_bound(ref32, ref64)[finite]
     assert (err <= bound).all(), "%s: max err %g vs bound %g (reference's own max err %g)" % (
-        what, err.max(), bound.min(), np.abs(np.asarray(ref32, np.float64) - ref64).max())
+        what, err.max(), bound.min(), np.abs(np.asarray(ref32, np.float64) - ref64)[finite].max())
 
 
 @pytest.mark.parametrize("name", KERNEL_CASES)
@@ -394,3 +397,71 @@ def test_forward_and_backward_capture_into_a_cuda_graph(pmr, oracle):
     assert_bits(image.cpu().numpy(), fresh[0].cpu().numpy(), "image (replay)")
     assert_bits(dv.cpu().numpy(), fresh_grads[0].cpu().numpy(), "d_vertices (replay)")
     assert_bits(da.cpu().numpy(), fresh_grads[1].cpu().numpy(), "d_attributes (replay)")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_scenes_vs_oracle(pmr, oracle, threshold, seed):
+    """Randomised sweep: image size (odd sizes, single rows / columns), triangle count, triangle scale from
+    sub-pixel to screen-filling, shared vertices, mixed-sign and tiny w, degenerate and duplicated triangles,
+    attribute counts with and without a specialised kernel -- everything bit-exact against the oracle
+    (forward buffers, image, ORDERED gradients), ATOMIC gradients within the summation-order bound."""
+    rng = np.random.default_rng(1000 + seed)
+    W, H = int(rng.choice([1, 7, 16, 33, 64, 97, 130])), int(rng.choice([1, 5, 16, 31, 64, 75, 128]))
+    B = int(rng.integers(1, 4))
+    A = int(rng.choice([1, 3, 4, 7, 9, 12, 13]))
+    kind = seed % 3
+    if kind == 0:        # soup of independent triangles, from sub-pixel to screen-filling
+        T = int(rng.integers(1, 900))
+        V = 3 * T
+        scale = float(rng.choice([0.01, 0.03, 0.1, 0.5, 2.0]))
+        centre = rng.uniform(-1.1, 1.1, (B, T, 1, 2))
+        xy = (centre + scale * rng.standard_normal((B, T, 3, 2))).reshape(B, V, 2)
+        tris = np.arange(V).reshape(T, 3)
+    elif kind == 1:      # jittered grid mesh: small triangles that share vertices and edges
+        n = int(rng.integers(3, 22))
+        V = n * n
+        gy, gx = np.meshgrid(np.linspace(-1.05, 1.05, n), np.linspace(-1.05, 1.05, n), indexing="ij")
+        xy = np.stack([gx, gy], 2).reshape(1, V, 2) + (0.6 / n) * rng.standard_normal((B, V, 2))
+        i, j = np.meshgrid(np.arange(n - 1), np.arange(n - 1), indexing="ij")
+        q = (i * n + j).reshape(-1)
+        tris = np.concatenate([np.stack([q, q + 1, q + n], 1), np.stack([q + 1, q + n + 1, q + n], 1)])
+        rng.shuffle(tris)
+        T = tris.shape[0]
+    else:                # random index triples over random vertices: large overlapping triangles
+        V = int(rng.integers(3, 400))
+        T = int(rng.integers(1, 600))
+        xy = rng.uniform(-1.3, 1.3, (B, V, 2))
+        tris = rng.integers(0, V, (T, 3))
+    z = rng.uniform(-1.2, 1.2, (B, V, 1))                       # some depths outside [-1, 1]
+    w = rng.uniform(0.3, 2.5, (B, V, 1))
+    if seed % 4 == 0:
+        w[rng.random((B, V, 1)) < 0.1] *= -1.0                  # vertices behind the eye
+    if seed % 4 == 1:
+        w[rng.random((B, V, 1)) < 0.05] = 1e-3                  # tiny w: huge projected coordinates
+    verts = (np.concatenate([xy, z, np.ones_like(z)], 2) * w).astype(np.float32)
+    tris = np.array(tris)
+    degenerate = rng.random(T) < 0.03
+    tris[degenerate, 2] = tris[degenerate, 0]                   # zero-area triangles
+    if T > 4:
+        tris[T - 1] = tris[0]                                   # an exact duplicate: equal depth, larger id wins
+    tris = tris.astype(np.int32)
+    attrs = rng.standard_normal((B, V, A)).astype(np.float32)
+    bg = rng.standard_normal(A).astype(np.float32)
+    g = rng.standard_normal((B, H, W, A)).astype(np.float32)
+
+    ref = oracle.rasterize_clip_space(verts, attrs, tris, W, H, bg, grad_out=g, f64_yardstick=True)
+    cv, at = dev(verts).requires_grad_(True), dev(attrs).requires_grad_(True)
+    with pmr.backward_mode("ordered"):
+        out, (ids, bary, zb) = pmr.rasterize_clip_space(cv, at, dev(tris), W, H, dev(bg), return_buffers=True)
+        out.backward(dev(g))
+    assert_bits(ids.cpu().numpy(), ref["ids"], "ids")
+    assert_bits(bary.detach().cpu().numpy(), ref["bary"], "bary")
+    assert_bits(zb.detach().cpu().numpy(), ref["z"], "z")
+    assert_bits(out.detach().cpu().numpy(), ref["out"], "out")
+    assert_bits(cv.grad.cpu().numpy(), ref["d_vertices"], "d_vertices (ordered)")
+    assert_bits(at.grad.cpu().numpy(), ref["d_attributes"], "d_attributes (ordered)")
+    cv2, at2 = dev(verts).requires_grad_(True), dev(attrs).requires_grad_(True)
+    with pmr.backward_mode("atomic"):
+        pmr.rasterize_clip_space(cv2, at2, dev(tris), W, H, dev(bg)).backward(dev(g))
+    atomic_close(at2.grad.cpu().numpy(), ref["d_attributes"], ref["d_attributes_f64"], "d_attributes (atomic)")
+    atomic_close(cv2.grad.cpu().numpy(), ref["d_vertices"], ref["d_vertices_f64"], "d_vertices (atomic)")
