@@ -188,6 +188,26 @@ PMR_API int pmr_shade_diffuse_backward(pmr_context *ctx, const float *grad_rgba,
                                        const float *ambient, int B, int L, int A, int image_width,
                                        int image_height, float *d_pixels, void *stream);
 
+/*
+ * The same with the specular term (render.py:326-372): pixels float32 [B,H,W,A], A = 12: [normal, position,
+ * diffuse, specular rgb] with `shininess` float32 [B] (one exponent per image), or A = 13 with the exponent in
+ * channel 12 (`shininess` ignored, may be NULL); camera_position float32 [B,3].  The reference divides the
+ * reflection . view products of each (image, light) by their L2 norm over all pixels of the image before the
+ * power: the forward pass returns those sums of squares in norm2 [B,L] (written by the call) and the backward
+ * pass takes them back, together with a scratch buffer sum_gx [B,L] it overwrites.  Gradients reach the
+ * pixel channels only (all 12 / 13 of them).
+ */
+PMR_API int pmr_shade_phong_forward(pmr_context *ctx, const float *pixels, const float *light_positions,
+                                    const float *light_intensities, const float *ambient,
+                                    const float *camera_position, const float *shininess,
+                                    int B, int L, int A, int image_width, int image_height,
+                                    float *norm2, float *rgba, void *stream);
+PMR_API int pmr_shade_phong_backward(pmr_context *ctx, const float *grad_rgba, const float *pixels,
+                                     const float *light_positions, const float *light_intensities,
+                                     const float *ambient, const float *camera_position, const float *shininess,
+                                     const float *norm2, int B, int L, int A, int image_width, int image_height,
+                                     float *sum_gx, float *d_pixels, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

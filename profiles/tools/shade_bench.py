@@ -26,8 +26,14 @@ def main():
     except Exception:
         pass
     P = B * H * W
+    px13 = torch.cat([px, torch.rand((B, H, W, 3), generator=g).cuda(), 1.0 + 9.0 * torch.rand((B, H, W, 1), generator=g).cuda()], 3)
+    cam = torch.randn((B, 3), generator=g).cuda() * 4
+    _, norm2 = ops.shade_phong_forward(px13, lp, li, None, cam, None)
+    # specular: two passes each way; bytes = what the two kernels of a call must move (13 channels = 52 B/px)
     for name, fn, nbytes in (("shade_diffuse_forward", lambda: ops.shade_diffuse_forward(px, lp, li, None), P * 52),
-                             ("shade_diffuse_backward", lambda: ops.shade_diffuse_backward(grad, px, lp, li, None), P * 88)):
+                             ("shade_diffuse_backward", lambda: ops.shade_diffuse_backward(grad, px, lp, li, None), P * 88),
+                             ("shade_phong_forward (norm pass + shade)", lambda: ops.shade_phong_forward(px13, lp, li, None, cam, None), P * (52 + 52 + 16)),
+                             ("shade_phong_backward (sums pass + gradient)", lambda: ops.shade_phong_backward(grad, px13, lp, li, None, cam, None, norm2), P * (68 + 68 + 52))):
         for _ in range(5):
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -413,4 +413,38 @@ int pmr_shade_diffuse_backward(pmr_context *ctx, const float *grad_rgba, const f
                                           W, H, d_pixels, (cudaStream_t)stream);
 }
 
+int pmr_shade_phong_forward(pmr_context *ctx, const float *pixels, const float *light_positions,
+                            const float *light_intensities, const float *ambient, const float *camera_position,
+                            const float *shininess, int B, int L, int A, int W, int H, float *norm2, float *rgba,
+                            void *stream) {
+  int rc = pmr::validate_common(ctx, B, 0, 0, W, H);
+  if (rc) return rc;
+  if (A < 12 || L < 0) return set_error(ctx, PMR_ERR_INVALID, "specular shading needs at least 12 pixel channels and L >= 0");
+  if (A == 12 && !shininess) return set_error(ctx, PMR_ERR_INVALID, "12 channels carry no shininess: pass it per image");
+  if (B == 0) return PMR_OK;
+  if (!pixels || !rgba || !norm2 || !camera_position || (L > 0 && (!light_positions || !light_intensities)))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(rgba)) return set_error(ctx, PMR_ERR_INVALID, "rgba must be 16-byte aligned");
+  return pmr::shade_phong_forward_impl(ctx, pixels, light_positions, light_intensities, ambient, camera_position,
+                                       A > 12 ? nullptr : shininess, B, L, A, W, H, norm2, rgba, (cudaStream_t)stream);
+}
+
+int pmr_shade_phong_backward(pmr_context *ctx, const float *grad_rgba, const float *pixels,
+                             const float *light_positions, const float *light_intensities, const float *ambient,
+                             const float *camera_position, const float *shininess, const float *norm2, int B, int L,
+                             int A, int W, int H, float *sum_gx, float *d_pixels, void *stream) {
+  int rc = pmr::validate_common(ctx, B, 0, 0, W, H);
+  if (rc) return rc;
+  if (A < 12 || L < 0) return set_error(ctx, PMR_ERR_INVALID, "specular shading needs at least 12 pixel channels and L >= 0");
+  if (A == 12 && !shininess) return set_error(ctx, PMR_ERR_INVALID, "12 channels carry no shininess: pass it per image");
+  if (B == 0) return PMR_OK;
+  if (!grad_rgba || !pixels || !d_pixels || !norm2 || !sum_gx || !camera_position ||
+      (L > 0 && (!light_positions || !light_intensities)))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(grad_rgba)) return set_error(ctx, PMR_ERR_INVALID, "grad_rgba must be 16-byte aligned");
+  return pmr::shade_phong_backward_impl(ctx, grad_rgba, pixels, light_positions, light_intensities, ambient,
+                                        camera_position, A > 12 ? nullptr : shininess, norm2, B, L, A, W, H, sum_gx,
+                                        d_pixels, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -100,4 +100,13 @@ int shade_diffuse_backward_impl(Context *ctx, const float *grad_rgba, const floa
                                 const float *light_positions, const float *light_intensities, const float *ambient,
                                 int B, int L, int A, int W, int H, float *d_pixels, cudaStream_t stream);
 
+int shade_phong_forward_impl(Context *ctx, const float *pixels, const float *light_positions,
+                             const float *light_intensities, const float *ambient, const float *camera,
+                             const float *shininess, int B, int L, int A, int W, int H, float *norm2, float *rgba,
+                             cudaStream_t stream);
+int shade_phong_backward_impl(Context *ctx, const float *grad_rgba, const float *pixels, const float *light_positions,
+                              const float *light_intensities, const float *ambient, const float *camera,
+                              const float *shininess, const float *norm2, int B, int L, int A, int W, int H,
+                              float *sum_gx, float *d_pixels, cudaStream_t stream);
+
 }  // namespace pmr

@@ -195,3 +195,48 @@ def shade_diffuse_backward(grad_rgba, pixels, light_positions, light_intensities
                                                     _lib.stream_ptr(px.device))
     _lib.check(ctx, rc)
     return d_pixels
+
+
+def shade_phong_forward(pixels, light_positions, light_intensities, ambient, camera_position, shininess):
+    """pixels [B,H,W,12|13] -> (RGBA [B,H,W,4] rows flipped, norm2 [B,L]); diffuse + ambient + specular."""
+    px = _require(pixels, torch.float32, "pixels")
+    lp = _require(light_positions, torch.float32, "light_positions")
+    li = _require(light_intensities, torch.float32, "light_intensities")
+    am = _require(ambient, torch.float32, "ambient_color") if ambient is not None else None
+    cam = _require(camera_position, torch.float32, "camera_position")
+    sh = _require(shininess, torch.float32, "shininess_coefficients") if shininess is not None else None
+    B, H, W, A = px.shape
+    L = lp.shape[1]
+    rgba = torch.empty((B, H, W, 4), dtype=torch.float32, device=px.device)
+    norm2 = torch.empty((B, L), dtype=torch.float32, device=px.device)
+    ctx = _lib.context(px.device.index)
+    with torch.cuda.device(px.device):
+        rc = _lib.load().pmr_shade_phong_forward(ctx, _lib.ptr(px), _lib.ptr(lp), _lib.ptr(li), _lib.ptr(am), _lib.ptr(cam),
+                                                 _lib.ptr(sh), B, L, A, W, H, _lib.ptr(norm2), _lib.ptr(rgba),
+                                                 _lib.stream_ptr(px.device))
+    _lib.check(ctx, rc)
+    return rgba, norm2
+
+
+def shade_phong_backward(grad_rgba, pixels, light_positions, light_intensities, ambient, camera_position, shininess,
+                         norm2):
+    """-> d_pixels [B,H,W,A]."""
+    g = _aligned(_require(grad_rgba, torch.float32, "grad_output"))
+    px = _require(pixels, torch.float32, "pixels")
+    lp = _require(light_positions, torch.float32, "light_positions")
+    li = _require(light_intensities, torch.float32, "light_intensities")
+    am = _require(ambient, torch.float32, "ambient_color") if ambient is not None else None
+    cam = _require(camera_position, torch.float32, "camera_position")
+    sh = _require(shininess, torch.float32, "shininess_coefficients") if shininess is not None else None
+    n2 = _require(norm2, torch.float32, "norm2")
+    B, H, W, A = px.shape
+    L = lp.shape[1]
+    d_pixels = torch.empty_like(px)
+    sums = torch.empty((B, L), dtype=torch.float32, device=px.device)
+    ctx = _lib.context(px.device.index)
+    with torch.cuda.device(px.device):
+        rc = _lib.load().pmr_shade_phong_backward(ctx, _lib.ptr(g), _lib.ptr(px), _lib.ptr(lp), _lib.ptr(li), _lib.ptr(am),
+                                                  _lib.ptr(cam), _lib.ptr(sh), _lib.ptr(n2), B, L, A, W, H,
+                                                  _lib.ptr(sums), _lib.ptr(d_pixels), _lib.stream_ptr(px.device))
+    _lib.check(ctx, rc)
+    return d_pixels

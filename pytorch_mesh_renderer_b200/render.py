@@ -41,6 +41,40 @@ def shade_diffuse(pixels, light_positions, light_intensities, ambient_color=None
                                light_intensities.contiguous().float(),
                                ambient_color.contiguous().float() if ambient_color is not None else None)
 
+class _ShadePhong(torch.autograd.Function):
+    """The same with the specular branch of render.py:326-372 (two kernels each way: the reference normalises the
+    reflection . view products by their L2 norm over the whole image)."""
+
+    @staticmethod
+    def forward(ctx, pixels, light_positions, light_intensities, ambient_color, camera_position, shininess):
+        rgba, norm2 = ops.shade_phong_forward(pixels, light_positions, light_intensities, ambient_color,
+                                              camera_position, shininess)
+        ctx.save_for_backward(pixels, light_positions, light_intensities, camera_position, norm2)
+        ctx.ambient, ctx.shininess = ambient_color, shininess
+        return rgba
+
+    @staticmethod
+    def backward(ctx, grad_rgba):
+        pixels, light_positions, light_intensities, camera_position, norm2 = ctx.saved_tensors
+        d_pixels = ops.shade_phong_backward(grad_rgba.contiguous(), pixels, light_positions, light_intensities,
+                                            ctx.ambient, camera_position, ctx.shininess, norm2)
+        return d_pixels, None, None, None, None, None
+
+
+def shade_phong(pixels, light_positions, light_intensities, camera_position, ambient_color=None, shininess=None):
+    """RGBA [B,H,W,4] (rows flipped) from `pixels` [B,H,W,12] = [normal, position, diffuse, specular] with
+    `shininess` [B] (or a scalar), or [B,H,W,13] with the exponent in channel 12; gradients flow to `pixels` only."""
+    B = pixels.shape[0]
+    if pixels.shape[3] == 12:
+        shininess = torch.as_tensor(shininess, dtype=torch.float32, device=pixels.device).reshape(-1).expand(B).contiguous()
+    else:
+        shininess = None
+    return _ShadePhong.apply(pixels.contiguous(), light_positions.contiguous().float(),
+                             light_intensities.contiguous().float(),
+                             ambient_color.contiguous().float() if ambient_color is not None else None,
+                             camera_position.contiguous().float(), shininess)
+
+
 # lights a fused-kernel call can take (csrc/shade.cu kMaxLights)
 _MAX_FUSED_LIGHTS = 16
 
@@ -130,8 +164,15 @@ def render(vertices, triangles, normals, diffuse_colors, camera_position, camera
 
     lights_need_grad = light_positions.requires_grad or light_intensities.requires_grad or (
         ambient_color is not None and ambient_color.requires_grad)
-    if specular_colors is None and not lights_need_grad and light_positions.shape[1] <= _MAX_FUSED_LIGHTS:
+    fusable = not lights_need_grad and light_positions.shape[1] <= _MAX_FUSED_LIGHTS
+    if specular_colors is None and fusable:
         image = shade_diffuse(pixels, light_positions, light_intensities, ambient_color)
+        return image.to(home) if home != device else image
+    if (specular_colors is not None and fusable and not camera_position.requires_grad
+            and (per_vertex_shininess or not shininess_coefficients.requires_grad)
+            and (per_vertex_shininess or shininess_coefficients.numel() in (1, batch))):
+        image = shade_phong(pixels, light_positions, light_intensities, camera_position, ambient_color,
+                            None if per_vertex_shininess else shininess_coefficients)
         return image.to(home) if home != device else image
 
     pixel_normals = F.normalize(pixels[..., 0:3], p=2, dim=3)

@@ -95,3 +95,83 @@ def test_render_uses_the_fused_shader_and_matches_reference(pmr):
     for mine, key in ((v.grad, "d_vertices"), (n.grad, "d_normals"), (d.grad, "d_diffuse")):
         ref = c[key]
         assert np.abs(mine.cpu().numpy() - ref).max() <= 2e-4 * (np.abs(ref).max() + 1e-12), key
+
+
+def _mirror_specular(pmr, px, lp, li, ambient, camera, shininess):
+    import torch.nn.functional as F
+    from pytorch_mesh_renderer_b200.render import phong_shader
+    normals = F.normalize(px[..., 0:3], p=2, dim=3)
+    mask = (px[..., 6:9] >= 0.0).any(dim=3).to(torch.float32)
+    shin = px[..., 12] if px.shape[3] > 12 else shininess.reshape(-1, 1, 1)
+    return phong_shader(normals, mask, px[..., 3:6], lp, li, px[..., 6:9], camera, px[..., 9:12], shin, ambient)
+
+
+@pytest.mark.parametrize("B,H,W,A,L,use_ambient", [(2, 37, 53, 12, 1, False), (3, 16, 40, 13, 3, True),
+                                                  (1, 64, 64, 13, 2, False), (2, 24, 24, 12, 4, True)])
+def test_shade_phong_matches_torch_mirror(pmr, B, H, W, A, L, use_ambient):
+    """Specular branch: two passes each way; the per-(image, light) sums are float atomics, so values are
+    compared by tolerance (1e-6 + 1e-5 relative; gradients also relative to their largest magnitude)."""
+    from pytorch_mesh_renderer_b200.render import shade_phong
+    g = torch.Generator().manual_seed(200 + L)
+    px = _random_pixels(B, H, W, A, seed=17 + A)
+    px[..., 9:12] = torch.rand((B, H, W, 3), generator=g)                 # specular colours
+    if A > 12:
+        px[..., 12] = 1.0 + 9.0 * torch.rand((B, H, W), generator=g)      # per-pixel shininess in [1, 10)
+    bg = px[..., 6] < 0
+    px[bg] = -1.0
+    px = px.cuda()
+    lp = (3.0 * torch.randn((B, L, 3), generator=g)).cuda()
+    li = torch.rand((B, L, 3), generator=g).cuda()
+    cam = (4.0 * torch.randn((B, 3), generator=g)).cuda()
+    ambient = torch.rand((B, 3), generator=g).cuda() if use_ambient else None
+    shininess = (2.0 + 6.0 * torch.rand((B,), generator=g)).cuda() if A == 12 else None
+    grad = torch.randn((B, H, W, 4), generator=g).cuda()
+
+    a = px.clone().requires_grad_(True)
+    out = shade_phong(a, lp, li, cam, ambient, shininess)
+    out.backward(grad)
+    b = px.clone().requires_grad_(True)
+    ref = _mirror_specular(pmr, b, lp, li, ambient, cam, shininess)
+    ref.backward(grad)
+
+    o, r = out.detach().cpu().numpy(), ref.detach().cpu().numpy()
+    assert np.array_equal(o[..., 3], r[..., 3])
+    assert (np.abs(o - r) <= 1e-6 + 1e-5 * np.abs(r)).all(), np.abs(o - r).max()
+    go, gr = a.grad.cpu().numpy(), b.grad.cpu().numpy()
+    go[0, 0, 0, 0:3] = gr[0, 0, 0, 0:3] = 0.0                             # the zero-normal pixel (0/0 in torch)
+    finite = np.isfinite(gr)
+    assert (np.isfinite(go) == finite).all()
+    err = np.abs(go - gr)[finite]
+    scale = np.abs(gr[finite]).max()
+    assert (err <= 1e-6 + 1e-5 * np.abs(gr[finite]) + 5e-6 * scale).all(), (err.max(), scale)
+
+
+@pytest.mark.parametrize("name", ["render_complex_vertex_shininess_96x72", "render_complex_scalar_shininess_96x72"])
+def test_render_specular_uses_the_fused_shader_and_matches_reference(pmr, name):
+    from pytorch_mesh_renderer_b200 import _lib
+    c = load_golden(name)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    v = dev(c["vertices"]).requires_grad_(True)
+    n = dev(c["normals"]).requires_grad_(True)
+    d = dev(c["diffuse"]).requires_grad_(True)
+    extra = {}
+    for k in c:
+        if k.startswith("arg_"):
+            val = c[k]
+            extra[k[4:]] = dev(val) if val.ndim > 0 else torch.tensor(float(val))
+    index = torch.cuda.current_device()
+    _lib.enable_stage_timing(index, True)
+    _lib.read_stage_timing(index, reset=True)
+    with pmr.backward_mode("ordered"):
+        out = pmr.render(v, dev(c["triangles"]), n, d, dev(c["eye"]), dev(c["center"]), dev(c["up"]),
+                         dev(c["light_positions"]), dev(c["light_intensities"]), int(c["width"]), int(c["height"]), **extra)
+        out.backward(dev(c["grad_out"]))
+    stages = _lib.read_stage_timing(index, reset=True)
+    _lib.enable_stage_timing(index, False)
+    assert stages["shade"][1] == 2                                         # the fused specular path ran (fwd + bwd)
+    img = out.detach().cpu().numpy()
+    assert np.array_equal(img[..., 3], c["image"][..., 3])
+    assert (np.abs(img - c["image"]) <= 1e-5 + 1e-4 * np.abs(c["image"])).all()
+    for mine, key in ((v.grad, "d_vertices"), (n.grad, "d_normals"), (d.grad, "d_diffuse")):
+        ref = c[key]
+        assert np.abs(mine.cpu().numpy() - ref).max() <= 2e-4 * (np.abs(ref).max() + 1e-12), key
