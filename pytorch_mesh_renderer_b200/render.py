@@ -2,10 +2,10 @@
 reference's src/mesh_renderer/render.py (render :16-228, phong_shader :231-386, tone_mapper :389-419),
 device-aware (everything stays on the device of `vertices`; the reference allocates on the CPU, SURVEY
 F11).  Rasterization and attribute interpolation run in the CUDA kernels of libpmr_b200.  The lighting of
-a `render` call without specular colours (diffuse + ambient: the reference's own cube test and BASELINE
-config c1) is ONE kernel forward and one backward (csrc/shade.cu, `shade_diffuse`); the specular branch
-(per-(image, light) normalisation over all pixels, render.py:347-353) and callers that need gradients
-with respect to the lights use the torch-op `phong_shader` below.  Everything is checked against outputs
+a `render` call is one kernel each way without specular colours (`shade_diffuse`: the reference's own cube test
+and BASELINE config c1) and two each way with them (`shade_phong`: the per-(image, light) normalisation over all
+pixels of render.py:347-353 is a reduction between the passes) -- csrc/shade.cu; callers that need gradients
+with respect to the lights, the camera or a per-image shininess use the torch-op `phong_shader` below.  Everything is checked against outputs
 of the unmodified reference (tests/golden/render_*.npz) and the reference's PNG fixtures.
 """
 import torch
