@@ -208,6 +208,28 @@ PMR_API int pmr_shade_phong_backward(pmr_context *ctx, const float *grad_rgba, c
                                      const float *norm2, int B, int L, int A, int image_width, int image_height,
                                      float *sum_gx, float *d_pixels, void *stream);
 
+/*
+ * The render path in one piece (render.py:183-228 for a call without specular colours): rasterize, interpolate
+ * the nine channels [normal, world position, diffuse colour] and light them, without ever storing the
+ * [B,H,W,9] attribute image: the forward writes ids / barycentrics / z and RGBA [B,H,W,4] (rows flipped), the
+ * backward goes from grad_rgba straight to d_vertices [B,V,4] and d_attributes [B,V,9] (atomic accumulation).
+ * attributes float32 [B,V,9]; background float32 [9] (render.py:197 passes -1); lights as in
+ * pmr_shade_diffuse_forward.  Results equal pmr_rasterize_interpolate_forward followed by
+ * pmr_shade_diffuse_forward bit for bit.
+ */
+PMR_API int pmr_render_diffuse_forward(pmr_context *ctx, const float *vertices, const float *attributes,
+                                       const int32_t *triangles, const float *background,
+                                       const float *light_positions, const float *light_intensities,
+                                       const float *ambient, int B, int V, int T, int L,
+                                       int image_width, int image_height,
+                                       int32_t *ids, float *bary, float *z, float *rgba, void *stream);
+PMR_API int pmr_render_diffuse_backward(pmr_context *ctx, const float *grad_rgba, const float *vertices,
+                                        const float *attributes, const int32_t *triangles, const float *background,
+                                        const float *light_positions, const float *light_intensities,
+                                        const float *ambient, const int32_t *ids, const float *bary,
+                                        int B, int V, int T, int L, int image_width, int image_height,
+                                        float *d_vertices, float *d_attributes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

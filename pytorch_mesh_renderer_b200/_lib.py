@@ -47,6 +47,10 @@ _PROTOTYPES = {
     "pmr_shade_phong_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pmr_shade_phong_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
                                                 _vp, _vp, _vp]),
+    "pmr_render_diffuse_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
+                                                  _vp, _vp, _vp, _vp, _vp]),
+    "pmr_render_diffuse_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                   _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pmr_rasterize_clip_space_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                                                      _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
 }

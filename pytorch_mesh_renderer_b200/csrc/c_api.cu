@@ -447,4 +447,41 @@ int pmr_shade_phong_backward(pmr_context *ctx, const float *grad_rgba, const flo
                                         d_pixels, (cudaStream_t)stream);
 }
 
+int pmr_render_diffuse_forward(pmr_context *ctx, const float *vertices, const float *attributes,
+                               const int32_t *triangles, const float *background, const float *light_positions,
+                               const float *light_intensities, const float *ambient, int B, int V, int T, int L,
+                               int W, int H, int32_t *ids, float *bary, float *z, float *rgba, void *stream) {
+  int rc = pmr::validate_common(ctx, B, V, T, W, H);
+  if (rc) return rc;
+  if (L < 0 || L > 16) return set_error(ctx, PMR_ERR_SIZE, "0 to 16 lights");
+  if (B == 0) return PMR_OK;
+  if (!ids || !bary || !z || !rgba || !background || (T > 0 && (!vertices || !triangles || !attributes)) ||
+      (L > 0 && (!light_positions || !light_intensities)))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(vertices) || !pmr::aligned16(rgba))
+    return set_error(ctx, PMR_ERR_INVALID, "vertices and rgba must be 16-byte aligned");
+  pmr::ShadeArgs shade = {light_positions, light_intensities, ambient, L, rgba, nullptr, background};
+  return pmr::forward_impl(ctx, vertices, triangles, B, V, T, W, H, ids, bary, z, attributes, background, 9, nullptr,
+                           (cudaStream_t)stream, &shade);
+}
+
+int pmr_render_diffuse_backward(pmr_context *ctx, const float *grad_rgba, const float *vertices,
+                                const float *attributes, const int32_t *triangles, const float *background,
+                                const float *light_positions, const float *light_intensities, const float *ambient,
+                                const int32_t *ids, const float *bary, int B, int V, int T, int L, int W, int H,
+                                float *d_vertices, float *d_attributes, void *stream) {
+  int rc = pmr::validate_common(ctx, B, V, T, W, H);
+  if (rc) return rc;
+  if (L < 0 || L > 16) return set_error(ctx, PMR_ERR_SIZE, "0 to 16 lights");
+  if (B == 0 || V == 0) return PMR_OK;
+  if (!grad_rgba || !vertices || !attributes || !ids || !bary || !background || (T > 0 && !triangles) ||
+      (L > 0 && (!light_positions || !light_intensities)))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  if (!pmr::aligned16(vertices) || !pmr::aligned16(grad_rgba))
+    return set_error(ctx, PMR_ERR_INVALID, "vertices and grad_rgba must be 16-byte aligned");
+  pmr::ShadeArgs shade = {light_positions, light_intensities, ambient, L, nullptr, grad_rgba, background};
+  return pmr::backward_impl(ctx, nullptr, nullptr, vertices, attributes, triangles, ids, bary, B, V, T, 9, W, H,
+                            d_vertices, d_attributes, PMR_BACKWARD_ATOMIC, (cudaStream_t)stream, &shade);
+}
+
 }  // extern "C"

@@ -73,10 +73,19 @@ int check_launch(Context *ctx, const char *what);
       return ::pmr::set_error((ctx), PMR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
   } while (0)
 
+// The render path: lights for shading inside the resolve / backward kernels (9 attribute channels).
+struct ShadeArgs {
+  const float *light_positions, *light_intensities, *ambient;   // [B,L,3], [B,L,3], [B,3] or nullptr
+  int L;
+  float *rgba;               // forward: [B,H,W,4] out
+  const float *grad_rgba;    // backward: [B,H,W,4] in
+  const float *background;   // backward: [9]
+};
+
 // raster_forward.cu
 int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, int V, int T, int W, int H,
                  int32_t *ids, float *bary, float *z, const float *attrs, const float *bg, int A,
-                 float *image, cudaStream_t stream);
+                 float *image, cudaStream_t stream, const ShadeArgs *shade = nullptr);
 int interpolate_impl(Context *ctx, const float *attrs, const int32_t *tris, const int32_t *ids,
                      const float *bary, const float *bg, int B, int V, int A, int W, int H, float *out,
                      cudaStream_t stream);
@@ -84,7 +93,7 @@ int interpolate_impl(Context *ctx, const float *attrs, const int32_t *tris, cons
 int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, const float *verts,
                   const float *attrs, const int32_t *tris, const int32_t *ids, const float *bary,
                   int B, int V, int T, int A, int W, int H, float *d_verts, float *d_attrs, int mode,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const ShadeArgs *shade = nullptr);
 
 // vertex_stage.cu
 int transform_forward_impl(Context *ctx, const float *matrices, const float *world, int B, int V, int shared,

@@ -17,6 +17,7 @@
 // reference op for op; compile with -fmad=false.
 #include "pmr_internal.cuh"
 #include "raster_math.cuh"
+#include "shade_math.cuh"
 
 namespace pmr {
 
@@ -195,12 +196,19 @@ __device__ __forceinline__ void red_add_if(bool ok, float *addr, float v) {
 // consecutive words of the same vertex rows, which the memory system merges per 32-byte sector
 // (profiles/microbench/atomics_bench.cu: 3.8x the lane rate of scattered atomics).
 
-template <bool FUSED, int A_STATIC, int kBlockWarps>
-__global__ void __launch_bounds__(kBlockWarps * 32, (kBlockWarps == 8 ? 5 : 8))
+// SHADE (render path, A = 9): `grad` is d(RGBA) [B,H,W,4] with flipped rows; the pixel's nine interpolated
+// channels are recomputed from the corner attributes (they were never stored) and the gradient passes through
+// the diffuse + ambient lighting (shade_math.cuh) before it enters the interpolation backward.
+template <bool FUSED, int A_STATIC, int kBlockWarps, bool SHADE = false>
+__global__ void __launch_bounds__(kBlockWarps * 32, (kBlockWarps == 8 ? (SHADE ? 4 : 5) : 8))
 backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__ verts,
                        const float *__restrict__ attrs, const int32_t *__restrict__ tris,
                        const int32_t *__restrict__ ids, const float *__restrict__ bary,
-                       int V, int W, int H, float *__restrict__ d_verts, float *__restrict__ d_attrs) {
+                       int V, int W, int H, float *__restrict__ d_verts, float *__restrict__ d_attrs,
+                       const float *__restrict__ light_positions = nullptr,
+                       const float *__restrict__ light_intensities = nullptr,
+                       const float *__restrict__ ambient = nullptr, int L = 0,
+                       const float *__restrict__ background = nullptr) {
   constexpr int A = A_STATIC;
   constexpr int NV = 9 + (FUSED ? 3 * A : 0);
   constexpr int STRIDE = (NV + 3) | 1;           // NV sums + 3 vertex ids, odd => conflict-free rows
@@ -210,9 +218,11 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
   __shared__ __align__(8) unsigned long long grad_ready[kBlockWarps];      // mbarriers of the bulk gradient loads
   static_assert(32 * STRIDE >= 32 * A, "gradient staging must fit the row area");
 
+  __shared__ Lights lights;
   // The CTA covers 2 x (kBlockWarps/2) pixel blocks: 16 pixels wide, 2*kBlockWarps rows high.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z;
+  if (SHADE) load_lights(lights, light_positions, light_intensities, ambient, b, L);     // block barrier inside
   const int x0 = (blockIdx.x * 2 + (warp & 1)) * 8, y0 = (blockIdx.y * (kBlockWarps / 2) + (warp >> 1)) * 4;
   if (x0 >= W || y0 >= H) return;
   const int ix = x0 + (lane & 7), iy = y0 + (lane >> 3);
@@ -241,7 +251,25 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
     for (int j = 0; j < 3; ++j) vid[j] = __ldg(tris + 3 * (size_t)id + j);
   }
   float4 pv0 = make_float4(0.f, 0.f, 0.f, 0.f), pv1 = pv0, pv2 = pv0;
-  if (FUSED) {
+  if constexpr (SHADE) {
+    if (id >= 0) {
+      const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
+      pv0 = __ldg(v4 + vid[0]); pv1 = __ldg(v4 + vid[1]); pv2 = __ldg(v4 + vid[2]);
+      // the pixel's interpolated channels, exactly as the forward pass computed them (rast.py:118-150)
+      const float alpha = coverage_alpha(bp[0], bp[1], bp[2]);
+      const float one_minus = 1.0f - alpha;
+      const float *c0 = attrs_b + (size_t)vid[0] * A, *c1 = attrs_b + (size_t)vid[1] * A, *c2 = attrs_b + (size_t)vid[2] * A;
+      float px[9];
+#pragma unroll
+      for (int a = 0; a < 9; ++a) {
+        const float img = __ldg(c0 + a) * bp[0] + __ldg(c1 + a) * bp[1] + __ldg(c2 + a) * bp[2];
+        px[a] = alpha * img + one_minus * __ldg(background + a);
+      }
+      const float4 g4 = reinterpret_cast<const float4 *>(grad)[((size_t)b * H + (H - 1 - iy)) * W + ix];
+      const float g[3] = {g4.x, g4.y, g4.z};
+      shade_diffuse_pixel_backward(px, px + 3, px + 6, g, lights, L, ambient != nullptr, g_local, g_local + 3, g_local + 6);
+    }
+  } else if (FUSED) {
     // Stage the block's gradient rows through shared memory: a block row is 8*A contiguous
     // floats, read as float4 when the image rows keep them 16-byte aligned.
     float *stage = rows;
@@ -507,7 +535,23 @@ backward_ordered_kernel(const float *__restrict__ grad, const float *__restrict_
 int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, const float *verts,
                   const float *attrs, const int32_t *tris, const int32_t *ids, const float *bary,
                   int B, int V, int T, int A, int W, int H, float *d_verts, float *d_attrs, int mode,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const ShadeArgs *shade) {
+  if (shade != nullptr) {
+    // render path: one kernel from d(RGBA) to the vertex / attribute gradients (atomic accumulation)
+    const long long n = (long long)B * V;
+    if (n == 0) return PMR_OK;
+    if (A != 9 || mode != PMR_BACKWARD_ATOMIC)
+      return set_error(ctx, PMR_ERR_INVALID, "the render backward needs 9 attribute channels and the atomic mode");
+    StageScope timed(ctx, PMR_STAGE_BACKWARD, stream);
+    if (d_verts) PMR_CUDA(ctx, cudaMemsetAsync(d_verts, 0, (size_t)n * 4 * sizeof(float), stream));
+    if (d_attrs) PMR_CUDA(ctx, cudaMemsetAsync(d_attrs, 0, (size_t)n * 9 * sizeof(float), stream));
+    if ((long long)W * H * B == 0 || T == 0) return PMR_OK;
+    backward_blocks_kernel<true, 9, 8, true><<<dim3((W + 15) / 16, (H + 15) / 16, B), 256, 0, stream>>>(
+        shade->grad_rgba, verts, attrs, tris, ids, bary, V, W, H, d_verts, d_attrs, shade->light_positions,
+        shade->light_intensities, shade->ambient, shade->L, shade->background);
+    ctx->launches += 1;
+    return check_launch(ctx, "backward_blocks_kernel (render)");
+  }
   const bool fused = grad_image != nullptr;
   const float *grad = fused ? grad_image : df_dbary;
   const long long ppi = (long long)W * H, total = ppi * B;

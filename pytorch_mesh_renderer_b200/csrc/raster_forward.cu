@@ -29,6 +29,7 @@
 // Neither list order nor atomic order can change a result, so the pass is deterministic.
 #include "pmr_internal.cuh"
 #include "raster_math.cuh"
+#include "shade_math.cuh"
 
 namespace pmr {
 
@@ -850,19 +851,26 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
 
 constexpr int kResolveWarps = 8;
 
-template <int A_STATIC>
+// SHADE: the render path (render.py:198-228 without specular colours).  The nine interpolated channels
+// [normal, world position, diffuse colour] of a pixel never leave the registers: they are lit right here
+// (shade_math.cuh) and only RGBA is written, rows flipped as phong_shader returns them (render.py:382-386).
+template <int A_STATIC, bool SHADE>
 __global__ void __launch_bounds__(kResolveWarps * 32)
 resolve_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int W, int H,
                const float *__restrict__ centers,
                const unsigned long long *__restrict__ keys,
                int32_t *__restrict__ out_ids, float *__restrict__ out_bary, float *__restrict__ out_z,
                const float *__restrict__ attrs, const float *__restrict__ background, int A_dyn,
-               float *__restrict__ out_image) {
+               float *__restrict__ out_image, const float *__restrict__ light_positions,
+               const float *__restrict__ light_intensities, const float *__restrict__ ambient, int L,
+               float4 *__restrict__ out_rgba) {
   __shared__ __align__(16) float stage_all[kResolveWarps][32 * 16];
+  __shared__ Lights lights;
   const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // the CTA covers a 16x16 pixel tile: 2 blocks across, 4 down
   const int b = blockIdx.z;
+  if (SHADE) load_lights(lights, light_positions, light_intensities, ambient, b, L);     // block barrier inside
   const int blk_x0 = (blockIdx.x * 2 + (warp & 1)) * 8, blk_y0 = (blockIdx.y * (kResolveWarps / 2) + (warp >> 1)) * 4;
   if (blk_x0 >= W || blk_y0 >= H) return;
   const int ix = blk_x0 + (lane & 7), iy = blk_y0 + (lane >> 3);
@@ -879,8 +887,34 @@ resolve_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris
   }
   // (Gathering the 3*A corner attributes here, together with the vertices, was measured: 60 registers
   // instead of 38 cost more occupancy than the shorter dependency chain gained: 0.355 -> 0.411 ms.)
-  block_epilogue<A_STATIC>(stage_all[warp], b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
-                           out_ids, out_bary, out_z, out_image);
+  if (!SHADE) {
+    block_epilogue<A_STATIC>(stage_all[warp], b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
+                             out_ids, out_bary, out_z, out_image);
+    return;
+  }
+  block_epilogue<0>(stage_all[warp], b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
+                    out_ids, out_bary, out_z, nullptr);
+  if (ix < W && iy < H) {
+    // the same interpolation as block_epilogue (rast.py:118-150), into registers
+    float px[9];
+    if (best.id < 0) {
+#pragma unroll
+      for (int a = 0; a < 9; ++a) px[a] = __ldg(background + a);
+    } else {
+      const float alpha = coverage_alpha(best.b0, best.b1, best.b2);
+      const float one_minus = 1.0f - alpha;
+      const float *at = attrs + (size_t)b * V * 9;
+      const float *c0 = at + (size_t)__ldg(tris + 3 * (size_t)best.id + 0) * 9;
+      const float *c1 = at + (size_t)__ldg(tris + 3 * (size_t)best.id + 1) * 9;
+      const float *c2 = at + (size_t)__ldg(tris + 3 * (size_t)best.id + 2) * 9;
+#pragma unroll
+      for (int a = 0; a < 9; ++a) {
+        const float img = __ldg(c0 + a) * best.b0 + __ldg(c1 + a) * best.b1 + __ldg(c2 + a) * best.b2;
+        px[a] = alpha * img + one_minus * __ldg(background + a);
+      }
+    }
+    out_rgba[((size_t)b * H + (H - 1 - iy)) * W + ix] = shade_diffuse_pixel(px, px + 3, px + 6, lights, L, ambient != nullptr);
+  }
 }
 
 // Standalone interpolation (rast.py:118-150) from existing id / barycentric buffers.
@@ -950,11 +984,11 @@ static int launch_raster(Context *ctx, const float *verts, const int32_t *tris, 
 
 int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, int V, int T, int W, int H,
                  int32_t *ids, float *bary, float *z, const float *attrs, const float *bg, int A,
-                 float *image, cudaStream_t stream) {
+                 float *image, cudaStream_t stream, const ShadeArgs *shade) {
   if (B == 0 || W == 0 || H == 0) return PMR_OK;
   const float half_w = (float)(0.5 * W), half_h = (float)(0.5 * H);
 
-  if (T <= ctx->small_mesh_threshold && T <= kTinyMeshMax) {
+  if (shade == nullptr && T <= ctx->small_mesh_threshold && T <= kTinyMeshMax) {
     // tiny mesh: one kernel, every tile walks all triangles and writes the outputs itself
     int rc0 = ctx->bins.reserve(ctx, 16);
     if (rc0) return rc0;
@@ -1011,9 +1045,14 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
     StageScope timed(ctx, PMR_STAGE_RESOLVE, stream);
     dim3 grid((W + 15) / 16, (H + 2 * kResolveWarps - 1) / (2 * kResolveWarps), B);
 #define PMR_RESOLVE(AS)                                                                                          \
-  resolve_kernel<AS><<<grid, kResolveWarps * 32, 0, stream>>>(verts, tris, V, W, H, centers, keys, ids,          \
-                                                              bary, z, attrs, bg, A, image)
-    if (image == nullptr) PMR_RESOLVE(0);
+  resolve_kernel<AS, false><<<grid, kResolveWarps * 32, 0, stream>>>(verts, tris, V, W, H, centers, keys, ids,   \
+                                                              bary, z, attrs, bg, A, image, nullptr, nullptr,    \
+                                                              nullptr, 0, nullptr)
+    if (shade != nullptr)
+      resolve_kernel<9, true><<<grid, kResolveWarps * 32, 0, stream>>>(
+          verts, tris, V, W, H, centers, keys, ids, bary, z, attrs, bg, 9, nullptr, shade->light_positions,
+          shade->light_intensities, shade->ambient, shade->L, reinterpret_cast<float4 *>(shade->rgba));
+    else if (image == nullptr) PMR_RESOLVE(0);
     else if (A == 4) PMR_RESOLVE(4);
     else if (A == 9) PMR_RESOLVE(9);
     else if (A == 12) PMR_RESOLVE(12);

@@ -240,3 +240,60 @@ def shade_phong_backward(grad_rgba, pixels, light_positions, light_intensities, 
                                                   _lib.ptr(sums), _lib.ptr(d_pixels), _lib.stream_ptr(px.device))
     _lib.check(ctx, rc)
     return d_pixels
+
+
+def render_diffuse_forward(vertices, attributes, triangles, background, light_positions, light_intensities, ambient,
+                           image_width, image_height):
+    """Fused rasterize + interpolate + diffuse/ambient lighting -> (RGBA [B,H,W,4] rows flipped, ids, bary, z)."""
+    v = _aligned(_require(vertices, torch.float32, "clip_space_vertices"))
+    a = _require(attributes, torch.float32, "attributes")
+    t = _require(triangles, torch.int32, "triangles")
+    bg = _require(background, torch.float32, "background_value")
+    lp = _require(light_positions, torch.float32, "light_positions")
+    li = _require(light_intensities, torch.float32, "light_intensities")
+    am = _require(ambient, torch.float32, "ambient_color") if ambient is not None else None
+    B, V, _ = v.shape
+    if a.shape[2] != 9:
+        raise ValueError("the fused render path takes 9 attribute channels [normal, position, diffuse colour]")
+    W, H = int(image_width), int(image_height)
+    dev = v.device
+    ids = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    bary = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+    z = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    rgba = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+    ctx = _lib.context(dev.index)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pmr_render_diffuse_forward(
+            ctx, _lib.ptr(v), _lib.ptr(a), _lib.ptr(t), _lib.ptr(bg), _lib.ptr(lp), _lib.ptr(li), _lib.ptr(am),
+            B, V, t.shape[0], lp.shape[1], W, H, _lib.ptr(ids), _lib.ptr(bary), _lib.ptr(z), _lib.ptr(rgba),
+            _lib.stream_ptr(dev))
+    _lib.check(ctx, rc)
+    return rgba, ids, bary, z
+
+
+def render_diffuse_backward(grad_rgba, vertices, attributes, triangles, background, light_positions,
+                            light_intensities, ambient, ids, bary, need_vertices=True, need_attributes=True):
+    """-> (d_vertices [B,V,4] or None, d_attributes [B,V,9] or None)."""
+    g = _aligned(_require(grad_rgba, torch.float32, "grad_output"))
+    v = _aligned(_require(vertices, torch.float32, "clip_space_vertices"))
+    a = _require(attributes, torch.float32, "attributes")
+    t = _require(triangles, torch.int32, "triangles")
+    bg = _require(background, torch.float32, "background_value")
+    lp = _require(light_positions, torch.float32, "light_positions")
+    li = _require(light_intensities, torch.float32, "light_intensities")
+    am = _require(ambient, torch.float32, "ambient_color") if ambient is not None else None
+    i = _require(ids, torch.int32, "px_triangle_ids")
+    b = _require(bary, torch.float32, "px_barycentric_coords")
+    B, V, _ = v.shape
+    H, W = i.shape[1], i.shape[2]
+    dev = v.device
+    dv = torch.empty((B, V, 4), dtype=torch.float32, device=dev) if need_vertices else None
+    da = torch.empty((B, V, 9), dtype=torch.float32, device=dev) if need_attributes else None
+    ctx = _lib.context(dev.index)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pmr_render_diffuse_backward(
+            ctx, _lib.ptr(g), _lib.ptr(v), _lib.ptr(a), _lib.ptr(t), _lib.ptr(bg), _lib.ptr(lp), _lib.ptr(li),
+            _lib.ptr(am), _lib.ptr(i), _lib.ptr(b), B, V, t.shape[0], lp.shape[1], W, H, _lib.ptr(dv), _lib.ptr(da),
+            _lib.stream_ptr(dev))
+    _lib.check(ctx, rc)
+    return dv, da

@@ -75,6 +75,48 @@ def shade_phong(pixels, light_positions, light_intensities, camera_position, amb
                              camera_position.contiguous().float(), shininess)
 
 
+class _RenderDiffuse(torch.autograd.Function):
+    """rasterize_clip_space + shade_diffuse as ONE pass each way: the resolve kernel lights the nine interpolated
+    channels while they are still in registers, the backward kernel recomputes them from the corner attributes --
+    the [B,H,W,9] attribute image and its gradient are never written (render.py:183-228)."""
+
+    @staticmethod
+    def forward(ctx, clip_vertices, attributes, triangles, background, light_positions, light_intensities,
+                ambient_color, image_width, image_height):
+        rgba, ids, bary, _z = ops.render_diffuse_forward(clip_vertices, attributes, triangles, background,
+                                                         light_positions, light_intensities, ambient_color,
+                                                         image_width, image_height)
+        ctx.save_for_backward(clip_vertices, attributes, triangles, background, light_positions, light_intensities,
+                              ids, bary)
+        ctx.ambient = ambient_color
+        return rgba
+
+    @staticmethod
+    def backward(ctx, grad_rgba):
+        v, a, t, bg, lp, li, ids, bary = ctx.saved_tensors
+        need_v, need_a = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dv = da = None
+        if need_v or need_a:
+            dv, da = ops.render_diffuse_backward(grad_rgba.contiguous(), v, a, t, bg, lp, li, ctx.ambient, ids, bary,
+                                                 need_vertices=need_v, need_attributes=need_a)
+        return dv, da, None, None, None, None, None, None, None
+
+
+def render_diffuse_clip_space(clip_vertices, attributes, triangles, light_positions, light_intensities,
+                              image_width, image_height, ambient_color=None, background_value=None):
+    """RGBA [B,H,W,4] of clip-space meshes whose nine per-vertex attributes are [normal, world position, diffuse
+    colour]: rasterize + interpolate + diffuse/ambient Phong in one fused pass each way (gradients: clip vertices
+    and attributes, accumulated atomically)."""
+    device = clip_vertices.device
+    if background_value is None:
+        background_value = torch.full((9,), -1.0, device=device)                       # render.py:197
+    return _RenderDiffuse.apply(clip_vertices.contiguous().float(), attributes.contiguous().float(),
+                                triangles.contiguous(), background_value.contiguous().float(),
+                                light_positions.contiguous().float(), light_intensities.contiguous().float(),
+                                ambient_color.contiguous().float() if ambient_color is not None else None,
+                                int(image_width), int(image_height))
+
+
 # lights a fused-kernel call can take (csrc/shade.cu kMaxLights)
 _MAX_FUSED_LIGHTS = 16
 
@@ -159,12 +201,20 @@ def render(vertices, triangles, normals, diffuse_colors, camera_position, camera
     clip_from_world = torch.matmul(projection, view)
 
     background = torch.full((vertex_attributes.shape[2],), -1.0, device=device)        # render.py:197
-    pixels = rasterize(vertices, vertex_attributes, triangles.to(device), clip_from_world, image_width,
-                       image_height, background)
-
     lights_need_grad = light_positions.requires_grad or light_intensities.requires_grad or (
         ambient_color is not None and ambient_color.requires_grad)
     fusable = not lights_need_grad and light_positions.shape[1] <= _MAX_FUSED_LIGHTS
+    from .rasterize_triangles_ext import get_backward_mode
+    if specular_colors is None and fusable and get_backward_mode() == "atomic":
+        # one fused pass each way: the attribute image is never materialised
+        clip = camera_utils.transform_homogeneous(clip_from_world, vertices)
+        image = render_diffuse_clip_space(clip, vertex_attributes, triangles.to(device), light_positions,
+                                          light_intensities, image_width, image_height, ambient_color, background)
+        return image.to(home) if home != device else image
+
+    pixels = rasterize(vertices, vertex_attributes, triangles.to(device), clip_from_world, image_width,
+                       image_height, background)
+
     if specular_colors is None and fusable:
         image = shade_diffuse(pixels, light_positions, light_intensities, ambient_color)
         return image.to(home) if home != device else image

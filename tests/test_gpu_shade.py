@@ -175,3 +175,78 @@ def test_render_specular_uses_the_fused_shader_and_matches_reference(pmr, name):
     for mine, key in ((v.grad, "d_vertices"), (n.grad, "d_normals"), (d.grad, "d_diffuse")):
         ref = c[key]
         assert np.abs(mine.cpu().numpy() - ref).max() <= 2e-4 * (np.abs(ref).max() + 1e-12), key
+
+
+def _scene_with_normals(B, size, n_lon=48, n_rings=47):
+    from pytorch_mesh_renderer_b200 import synthetic as S
+    sc = S.sphere_views(n_lon, n_rings, B, size)
+    world = sc["world_vertices"].astype(np.float32)
+    normals = world / np.linalg.norm(world, axis=1, keepdims=True)
+    rng = np.random.default_rng(5)
+    diffuse = rng.random(world.shape, dtype=np.float32)
+    attrs = np.concatenate([normals, world, diffuse], 1)[None].repeat(B, 0).astype(np.float32)
+    return sc, attrs
+
+
+@pytest.mark.parametrize("size,use_ambient,L", [(96, False, 1), (131, True, 3)])
+def test_fused_render_path_equals_rasterize_then_shade(pmr, size, use_ambient, L):
+    """pmr_render_diffuse_*: lighting inside the resolve / backward kernels.  Forward: RGBA, ids, barycentrics
+    bit-identical to rasterize_clip_space followed by shade_diffuse.  Backward (atomic accumulation): against
+    the unfused ORDERED gradients, relative to their largest magnitude."""
+    from pytorch_mesh_renderer_b200 import ops
+    from pytorch_mesh_renderer_b200.render import render_diffuse_clip_space, shade_diffuse
+    B = 3
+    sc, attrs = _scene_with_normals(B, size)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    g = torch.Generator().manual_seed(9)
+    lp = (3.0 * torch.randn((B, L, 3), generator=g)).cuda()
+    li = torch.rand((B, L, 3), generator=g).cuda()
+    ambient = torch.rand((B, 3), generator=g).cuda() if use_ambient else None
+    grad = torch.randn((B, size, size, 4), generator=g).cuda()
+    tris = dev(sc["triangles"])
+    bg = torch.full((9,), -1.0, device="cuda")
+
+    cv = dev(sc["clip_vertices"]).requires_grad_(True)
+    at = dev(attrs).requires_grad_(True)
+    fused = render_diffuse_clip_space(cv, at, tris, lp, li, size, size, ambient)
+    fused.backward(grad)
+
+    cv2 = dev(sc["clip_vertices"]).requires_grad_(True)
+    at2 = dev(attrs).requires_grad_(True)
+    with pmr.backward_mode("ordered"):
+        pixels, (ids, bary, z) = pmr.rasterize_clip_space(cv2, at2, tris, size, size, bg, return_buffers=True)
+        unfused = shade_diffuse(pixels, lp, li, ambient)
+        unfused.backward(grad)
+
+    assert torch.equal(fused.detach(), unfused.detach())                     # bit-identical image
+    f_rgba, f_ids, f_bary, f_z = ops.render_diffuse_forward(cv.detach(), at.detach(), tris, bg, lp, li, ambient, size, size)
+    assert torch.equal(f_ids, ids) and torch.equal(f_bary, bary.detach()) and torch.equal(f_z, z.detach())
+    for mine, ref, what in ((cv.grad, cv2.grad, "d_clip_vertices"), (at.grad, at2.grad, "d_attributes")):
+        mine, ref = mine.cpu().numpy(), ref.cpu().numpy()
+        assert np.abs(mine - ref).max() <= 2e-5 * (np.abs(ref).max() + 1e-12), (what, np.abs(mine - ref).max(), np.abs(ref).max())
+
+
+def test_render_default_mode_takes_the_fused_path_and_matches_reference(pmr):
+    """render() in the default (atomic) mode: scatter / resolve+shade forward, one backward kernel; against the
+    unmodified reference's outputs (tests/golden/render_cube_96x72.npz)."""
+    from pytorch_mesh_renderer_b200 import _lib
+    c = load_golden("render_cube_96x72")
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    v = dev(c["vertices"]).requires_grad_(True)
+    n = dev(c["normals"]).requires_grad_(True)
+    d = dev(c["diffuse"]).requires_grad_(True)
+    index = torch.cuda.current_device()
+    _lib.enable_stage_timing(index, True)
+    _lib.read_stage_timing(index, reset=True)
+    out = pmr.render(v, dev(c["triangles"]), n, d, dev(c["eye"]), dev(c["center"]), dev(c["up"]),
+                     dev(c["light_positions"]), dev(c["light_intensities"]), int(c["width"]), int(c["height"]))
+    out.backward(dev(c["grad_out"]))
+    stages = _lib.read_stage_timing(index, reset=True)
+    _lib.enable_stage_timing(index, False)
+    assert stages["shade"][1] == 0 and stages["resolve"][1] == 1 and stages["backward"][1] == 1
+    img = out.detach().cpu().numpy()
+    assert np.array_equal(img[..., 3], c["image"][..., 3])
+    assert (np.abs(img - c["image"]) <= 1e-5 + 1e-4 * np.abs(c["image"])).all()
+    for mine, key in ((v.grad, "d_vertices"), (n.grad, "d_normals"), (d.grad, "d_diffuse")):
+        ref = c[key]
+        assert np.abs(mine.cpu().numpy() - ref).max() <= 2e-4 * (np.abs(ref).max() + 1e-12), key
