@@ -12,7 +12,7 @@
 
 namespace pmr {
 
-// Screen tile of the binning pass and of one raster CTA: 16x16 pixels = 8 warps x (8x4) pixels.
+// Screen tile of the large-triangle pass (one CTA at a time): 16x16 pixels = 8 warps x (8x4) pixels.
 constexpr int kTileW = 16, kTileH = 16, kTileShiftX = 4, kTileShiftY = 4;
 
 struct Context;
@@ -35,7 +35,7 @@ struct StageInterval {
 struct Context {
   int device = 0;
   int sm_count = 148;
-  int small_mesh_threshold = 64;      // T at or below this: no binning, every tile walks all triangles
+  int small_mesh_threshold = 64;      // T at or below this: the tile kernel alone, every tile walks all triangles
   Buffer bins, scratch, keys, centers;
   int centers_w = -1, centers_h = -1;  // image size the pixel-centre table was built for
   // host entry point: uploads and downloads run on their own streams beside the caller's (kernels)

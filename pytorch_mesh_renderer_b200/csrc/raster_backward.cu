@@ -2,10 +2,12 @@
 // optionally fused with the backward of the attribute interpolation (autograd of
 // rast.py:118-150), in two accumulation modes:
 //
-//   PMR_BACKWARD_ATOMIC   one thread per pixel; a warp whose covered pixels all belong to one
-//                         triangle reduces its 9 (+3A) sums with shuffles and issues one set of
-//                         atomics, otherwise lanes scatter individually.  fp32 sums in arbitrary
-//                         order.
+//   PMR_BACKWARD_ATOMIC   backward_blocks_kernel: one warp per 8x4 pixel block; the per-pixel sums are
+//                         parked in shared memory, rows sorted by triangle, and lane c adds column c
+//                         over each triangle's rows: one fire-and-forget atomic per (block, triangle,
+//                         column).  fp32 sums in arbitrary order.  (Attribute counts without a
+//                         specialised instance fall back to backward_atomic_kernel, one thread per
+//                         pixel.)  With SHADE it is also the backward of the fused render path.
 //   PMR_BACKWARD_ORDERED  one warp per (image, vertex): walks the union of the pixel boxes of the
 //                         vertex's triangles in ascending pixel order, lanes evaluate the
 //                         per-pixel terms in parallel and the sums are then folded strictly in

@@ -11,18 +11,22 @@
 //                         depth, and each one does atomicMin on the pixel's key in global memory (L2).
 //                         No per-tile duplication of triangle setup, no binning for these triangles.
 //                         Larger triangles are appended (id + pixel box) to the image's LARGE list.
-//   raster_tile_kernel    persistent CTAs walk the 16x16 screen tiles of the images that have large
-//                         triangles: the image's large list is scanned with a box-vs-tile test, the
-//                         survivors are staged 256 at a time as setup records in shared memory, a warp
-//                         per 8x4 pixel block culls them with a ballot, one lane per pixel keeps its
-//                         winner in registers (parts of large triangles that are small inside the tile
-//                         take the segment path on a shared-memory key), result merged into the global
-//                         keys.  Images without large triangles cost one load per tile; the whole
-//                         pass needs no host round trip (no list sizes to read back).
+//   raster_tile_kernel    persistent CTAs take (image, 64x64 macro tile) items of the images that have
+//                         large triangles from a work counter: the image's large list is scanned once
+//                         per macro tile with a box test into shared memory, each 16x16 screen tile
+//                         filters that short list, the survivors are staged 256 at a time as setup
+//                         records and walked front to back by a tile-level depth bound; a warp per 8x4
+//                         pixel block culls them (box, hierarchical z, conservative edge test) with a
+//                         ballot, one lane per pixel keeps its winner in registers (in a mesh of small
+//                         triangles the ones that are small inside the tile take the segment path on a
+//                         shared-memory key), result merged into the global keys.  Images without large
+//                         triangles cost one counter load per CTA; the whole pass needs no host round
+//                         trip (no list sizes to read back).
 //   resolve_kernel        one warp per 8x4 pixel block: decodes the winner, re-evaluates its
 //                         barycentrics / depth once (same arithmetic, same bits), interpolates the
-//                         attributes and stores ids / z / barycentrics / image as 16-byte vectors
-//                         through a shared-memory transpose.
+//                         attributes and stores ids / z as full sectors, barycentrics / image through a
+//                         shared-memory transpose and the bulk-copy engine.  With SHADE (render path)
+//                         the nine interpolated channels are lit in registers and only RGBA is written.
 // Meshes with few triangles (<= small_mesh_threshold) run raster_tile_kernel alone: every tile walks
 // the whole triangle array and writes the outputs itself.
 //
@@ -34,7 +38,7 @@
 namespace pmr {
 
 // ---------------------------------------------------------------------------------------------
-// Binning
+// Pixel boxes
 // ---------------------------------------------------------------------------------------------
 
 // Pixel box packed as four uint16: x = left | right << 16, y = bottom | top << 16 (W, H <= 32768).
