@@ -776,7 +776,7 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
       edge_values(m, __ldg(cx + x), __ldg(cy + y), e);
       edges_inside(e, esum);
       if (fragment_depth(e, esum, zc, wc, bc, z))
-        atomicMin(keys_b + (size_t)y * W + x, depth_key(z, __float_as_int(q0.w)));
+        atomicMin(keys_b + (unsigned)(y * W + x), depth_key(z, __float_as_int(q0.w)));   // H * W <= 2^30
     }
   };
 
@@ -813,13 +813,13 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
         const float4 q0 = sm.r0[j], q1 = sm.r1[j], q2 = sm.r2[j];
         const float m[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
         const int2 org = sm.origin[j];
-        const float cyv = __ldg(cy + org.y + dy);
-        const float *cxp = cx + org.x + dx;
+        const int yi = org.y + dy, xi = org.x + dx;      // 32-bit indices: one IMAD.WIDE per table
+        const float cyv = __ldg(centers + (W + yi));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (k < width) {
             float e[3], esum;
-            edge_values(m, __ldg(cxp + k), cyv, e);
+            edge_values(m, __ldg(centers + (xi + k)), cyv, e);
             if (edges_inside(e, esum)) inside |= 1u << k;
           }
         }
