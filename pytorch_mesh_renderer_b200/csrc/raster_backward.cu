@@ -202,7 +202,7 @@ __device__ __forceinline__ void red_add_if(bool ok, float *addr, float v) {
 // channels are recomputed from the corner attributes (they were never stored) and the gradient passes through
 // the diffuse + ambient lighting (shade_math.cuh) before it enters the interpolation backward.
 template <bool FUSED, int A_STATIC, int kBlockWarps, bool SHADE = false>
-__global__ void __launch_bounds__(kBlockWarps * 32, (kBlockWarps == 8 ? (SHADE ? 4 : 5) : 8))
+__global__ void __launch_bounds__(kBlockWarps * 32, (kBlockWarps == 8 ? (SHADE ? 4 : 5) : (A_STATIC == 9 ? 10 : 8)))
 backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__ verts,
                        const float *__restrict__ attrs, const int32_t *__restrict__ tris,
                        const int32_t *__restrict__ ids, const float *__restrict__ bary,
@@ -569,7 +569,7 @@ int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, 
   backward_blocks_kernel<F, AS, WARPS><<<dim3((W + 15) / 16, (H + 2 * WARPS - 1) / (2 * WARPS), B), WARPS * 32, 0, stream>>>(  \
       grad, verts, attrs, tris, ids, bary, V, W, H, d_verts, d_attrs)
     if (!fused) PMR_BLOCKS(false, 1, 8);
-    else if (A == 9) PMR_BLOCKS(true, 9, 8);
+    else if (A == 9) PMR_BLOCKS(true, 9, 4);      // CTAs of 4 warps (16x8 pixels): 0.622 -> 0.601 ms on c2; 2 warps: 0.620
     else if (A == 4) PMR_BLOCKS(true, 4, 8);
     else if (A == 12) PMR_BLOCKS(true, 12, 4);
     else if (A == 13) PMR_BLOCKS(true, 13, 4);

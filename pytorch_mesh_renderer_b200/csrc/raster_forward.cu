@@ -710,6 +710,7 @@ struct ScatterWarpSmem {
   unsigned short hits[160];                  // queue of inside pixels: slot | dy << 5 | x offset << 9
 };
 
+// (48 registers, 5 CTAs per SM; forcing 6 CTAs -- 40 registers, small spills -- measured 2 % slower.)
 __global__ void __launch_bounds__(kScatterWarps * 32)
 scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int T, int W, int H,
                      float half_w, float half_h, const float *__restrict__ centers,
@@ -859,7 +860,7 @@ constexpr int kResolveWarps = 8;
 // [normal, world position, diffuse colour] of a pixel never leave the registers: they are lit right here
 // (shade_math.cuh) and only RGBA is written, rows flipped as phong_shader returns them (render.py:382-386).
 template <int A_STATIC, bool SHADE>
-__global__ void __launch_bounds__(kResolveWarps * 32)
+__global__ void __launch_bounds__(kResolveWarps * 32, SHADE ? 5 : 8)
 resolve_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int W, int H,
                const float *__restrict__ centers,
                const unsigned long long *__restrict__ keys,
