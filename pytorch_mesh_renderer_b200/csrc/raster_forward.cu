@@ -225,19 +225,17 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
   if (bulk) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy reads
     __syncwarp();
-    if (lane == 0) {
-      float *bary_row = out_bary + 3 * p0, *image_row = out_image != nullptr ? out_image + p0 * A : nullptr;
+    // Eight lanes issue one row each in the same instruction (lanes 0..3: barycentric rows, 4..7: image rows)
+    // and wait for their own bulk group; issuing all eight from one lane cost a quarter of the kernel's
+    // instructions (ncu, profiles/r01/lines_r1c_*).
+    if (lane < 8 && (lane < 4 || out_image != nullptr)) {
+      const int r = lane & 3;
+      const bool is_image = lane >= 4;
+      const size_t row_pixel = p0 + (size_t)r * W;
+      float *dst = is_image ? out_image + row_pixel * A : out_bary + 3 * row_pixel;
       const unsigned stage_at = (unsigned)__cvta_generic_to_shared(stage);
-      const int bary_pitch = 3 * W, image_pitch = W * A;                // floats per image row
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        bulk_store_row(bary_row, stage_at + r * 96, 96u);
-        bary_row += bary_pitch;
-        if (out_image != nullptr) {
-          bulk_store_row(image_row, stage_at + 4 * (kImageAt + r * 8 * A), 32u * (unsigned)A);
-          image_row += image_pitch;
-        }
-      }
+      const unsigned src = stage_at + (is_image ? 4u * (unsigned)(kImageAt + r * 8 * A) : 96u * (unsigned)r);
+      bulk_store_row(dst, src, is_image ? 32u * (unsigned)A : 96u);
       bulk_store_commit_and_wait();
     }
     return;
