@@ -287,11 +287,12 @@ backward_blocks_kernel(const float *__restrict__ grad, const float *__restrict__
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(n_rows * 32 * A)) : "memory");
-        for (int r = 0; r < n_rows; ++r) {
-          const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + r * 8 * A);
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(dst), "l"(block_grad + (size_t)r * W * A), "r"((unsigned)(32 * A)), "r"(bar) : "memory");
-        }
+      }
+      __syncwarp();                               // barrier initialised and armed before the copies are issued
+      if (lane < n_rows) {                        // one row per lane, all issued by the same instruction
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + lane * 8 * A);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(block_grad + (size_t)lane * W * A), "r"((unsigned)(32 * A)), "r"(bar) : "memory");
       }
       if (id >= 0) {
         const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
