@@ -170,6 +170,32 @@ PMR_API int pmr_transform_backward(pmr_context *ctx, const float *matrices, cons
                                    int B, int V, int shared, float *d_world_vertices, void *stream);
 
 /*
+ * Vertex normals of a triangle mesh (reference src/common/meshes.py:3-35 compute_vertex_normals; SURVEY.md
+ * section 8f row 4) for loops that move the geometry every step.
+ *
+ * pmr_vertex_incidence turns the topology, ONCE, into the table both directions gather through:
+ * offsets int32 [V+1] and incidence int32 [3T], row v = the (corner, triangle) pairs with
+ * triangles[triangle][corner] == v, coded corner << 30 | triangle and sorted ascending -- the order in which
+ * the reference's three index_add_ passes (meshes.py:23-33) reach the vertex.  T < 2^30; vertex ids outside
+ * [0, V) are skipped (the reference raises an index error).
+ *
+ * pmr_vertex_normals_forward: vertices float32 [B,V,3] -> normals float32 [B,V,3] (normalised with
+ * eps = 1e-6, meshes.py:34) and, when raw != NULL, the summed un-normalised normals [B,V,3] that the backward
+ * needs.  Sums run in the reference's order with torch's CPU arithmetic, so the result is bit-reproducible.
+ * pmr_vertex_normals_backward: grad_normals [B,V,3] -> d_vertices [B,V,3]; grad_raw [B,V,3] is caller-provided
+ * scratch (the gradient at the un-normalised normals).  No atomics in either direction.
+ */
+PMR_API int pmr_vertex_incidence(pmr_context *ctx, const int32_t *triangles, int T, int V, int32_t *offsets,
+                                 int32_t *incidence, void *stream);
+PMR_API int pmr_vertex_normals_forward(pmr_context *ctx, const float *vertices, const int32_t *triangles,
+                                       const int32_t *offsets, const int32_t *incidence, int B, int V, int T,
+                                       float *raw, float *normals, void *stream);
+PMR_API int pmr_vertex_normals_backward(pmr_context *ctx, const float *grad_normals, const float *raw,
+                                        const float *vertices, const int32_t *triangles, const int32_t *offsets,
+                                        const int32_t *incidence, int B, int V, int T, float *grad_raw,
+                                        float *d_vertices, void *stream);
+
+/*
  * Direct caller of the path: per-pixel Phong lighting, diffuse + ambient terms, of the interpolated
  * attribute image (reference src/mesh_renderer/render.py:201-228 + phong_shader :231-386 for a
  * `render` call without specular colours).  pixels float32 [B,H,W,A], A >= 9, channels

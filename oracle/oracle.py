@@ -49,6 +49,8 @@ def lib():
                                                  ctypes.c_int, ctypes.c_int, ctypes.c_int64,
                                                  _f32p, _f32p]
         L.pmr_oracle_interp_backward.restype = None
+        L.pmr_oracle_vertex_normals.argtypes = [_f32p, _i32p, ctypes.c_int, ctypes.c_int, _f32p, _f32p]
+        L.pmr_oracle_vertex_normals.restype = None
         _lib = L
     return _lib
 
@@ -183,3 +185,14 @@ def rasterize_clip_space(clip_space_vertices, attributes, triangles, image_width
                 res["d_attributes_f64"].append(
                     interp_backward_attributes_f64acc(grad_out[b], tr, ids, bary, cv.shape[1]))
     return {k: np.stack(v) for k, v in res.items()}
+
+
+def vertex_normals(vertices, triangles, return_raw=False):
+    """compute_vertex_normals (src/common/meshes.py:3-35), batched like the reference: vertices [B,V,3]."""
+    v, t = _f32(vertices), _i32(triangles)
+    assert v.ndim == 3 and v.shape[2] == 3
+    normals, raw = np.empty_like(v), np.empty_like(v)
+    for b in range(v.shape[0]):
+        lib().pmr_oracle_vertex_normals(_p(v[b], _f32p), _p(t, _i32p), v.shape[1], t.shape[0],
+                                        _p(raw[b], _f32p), _p(normals[b], _f32p))
+    return (normals, raw) if return_raw else normals

@@ -392,3 +392,49 @@ void pmr_oracle_interp_backward(const float *g, const float *attrs, const int32_
     }
     free(prod);
 }
+
+/*
+ * compute_vertex_normals for ONE mesh -- src/common/meshes.py:3-35.
+ *
+ * The reference runs three index_add_ passes, one per triangle corner c (meshes.py:23-33), each over the
+ * triangles in ascending order, adding cross(p[c+1] - p[c], p[c+2] - p[c]) (corner indices mod 3) to the row
+ * of vertex triangles[t][c]; then torch.nn.functional.normalize(eps=1e-6, p=2, dim=-1) (meshes.py:34).
+ * torch's CPU kernels contract: cross = fma(a_p, b_q, -(a_q * b_p)) (the second product rounded first) and
+ * the squared norm of a contiguous row = fma(z, z, fma(y, y, x * x)) -- probed on torch 2.11 and pinned against
+ * the reference function itself by tests/test_oracle_golden.py.  This file is compiled with
+ * -ffp-contract=off, so the fused operations are the explicit fmaf calls and nothing else.
+ * raw [V,3] (may be NULL) receives the un-normalised sums.
+ */
+static void cross_torch(const float *a, const float *b, float *o)
+{
+    o[0] = fmaf(a[1], b[2], -(a[2] * b[1]));
+    o[1] = fmaf(a[2], b[0], -(a[0] * b[2]));
+    o[2] = fmaf(a[0], b[1], -(a[1] * b[0]));
+}
+
+void pmr_oracle_vertex_normals(const float *verts, const int32_t *tris, int V, int T, float *raw, float *normals)
+{
+    float *sum = (float *)calloc((size_t)(V > 0 ? V : 1) * 3, sizeof(float));
+    for (int c = 0; c < 3; ++c) {
+        for (int t = 0; t < T; ++t) {
+            const int32_t i0 = tris[3 * t + c], i1 = tris[3 * t + (c + 1) % 3], i2 = tris[3 * t + (c + 2) % 3];
+            float a[3], b[3], n[3];
+            for (int k = 0; k < 3; ++k) {
+                a[k] = verts[3 * (size_t)i1 + k] - verts[3 * (size_t)i0 + k];
+                b[k] = verts[3 * (size_t)i2 + k] - verts[3 * (size_t)i0 + k];
+            }
+            cross_torch(a, b, n);
+            for (int k = 0; k < 3; ++k) sum[3 * (size_t)i0 + k] += n[k];
+        }
+    }
+    for (int v = 0; v < V; ++v) {
+        const float *s = sum + 3 * (size_t)v;
+        const float norm = sqrtf(fmaf(s[2], s[2], fmaf(s[1], s[1], s[0] * s[0])));
+        const float d = norm > 1e-6f ? norm : 1e-6f;
+        for (int k = 0; k < 3; ++k) {
+            if (raw) raw[3 * (size_t)v + k] = s[k];
+            normals[3 * (size_t)v + k] = s[k] / d;
+        }
+    }
+    free(sum);
+}

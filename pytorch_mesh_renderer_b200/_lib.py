@@ -42,6 +42,9 @@ _PROTOTYPES = {
                                                           _vp, _vp, _i, _vp]),
     "pmr_transform_forward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "pmr_transform_backward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "pmr_vertex_incidence": (ctypes.c_int, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "pmr_vertex_normals_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "pmr_vertex_normals_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pmr_shade_diffuse_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pmr_shade_diffuse_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pmr_shade_phong_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -385,6 +385,44 @@ int pmr_transform_backward(pmr_context *ctx, const float *matrices, const float 
                                       (cudaStream_t)stream);
 }
 
+int pmr_vertex_incidence(pmr_context *ctx, const int32_t *triangles, int T, int V, int32_t *offsets,
+                         int32_t *incidence, void *stream) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (T < 0 || V < 0) return set_error(ctx, PMR_ERR_INVALID, "negative vertex/triangle count");
+  if (T >= (1 << 30)) return set_error(ctx, PMR_ERR_SIZE, "more than 2^30 triangles");
+  if (!offsets || (T > 0 && (!triangles || !incidence))) return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  return pmr::vertex_incidence_impl(ctx, triangles, T, V, offsets, incidence, (cudaStream_t)stream);
+}
+
+int pmr_vertex_normals_forward(pmr_context *ctx, const float *vertices, const int32_t *triangles,
+                               const int32_t *offsets, const int32_t *incidence, int B, int V, int T, float *raw,
+                               float *normals, void *stream) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (B < 0 || V < 0 || T < 0) return set_error(ctx, PMR_ERR_INVALID, "negative batch/vertex/triangle count");
+  if (B > 65535) return set_error(ctx, PMR_ERR_SIZE, "more than 65535 meshes per call (the mesh index is a grid dimension)");
+  if (B == 0 || V == 0) return PMR_OK;
+  if (!vertices || !offsets || !normals || (T > 0 && (!triangles || !incidence)))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  return pmr::vertex_normals_forward_impl(ctx, vertices, triangles, offsets, incidence, B, V, raw, normals,
+                                          (cudaStream_t)stream);
+}
+
+int pmr_vertex_normals_backward(pmr_context *ctx, const float *grad_normals, const float *raw, const float *vertices,
+                                const int32_t *triangles, const int32_t *offsets, const int32_t *incidence, int B,
+                                int V, int T, float *grad_raw, float *d_vertices, void *stream) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (B < 0 || V < 0 || T < 0) return set_error(ctx, PMR_ERR_INVALID, "negative batch/vertex/triangle count");
+  if (B > 65535) return set_error(ctx, PMR_ERR_SIZE, "more than 65535 meshes per call (the mesh index is a grid dimension)");
+  if (B == 0 || V == 0) return PMR_OK;
+  if (!grad_normals || !raw || !vertices || !offsets || !grad_raw || !d_vertices || (T > 0 && (!triangles || !incidence)))
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  return pmr::vertex_normals_backward_impl(ctx, grad_normals, raw, vertices, triangles, offsets, incidence, B, V,
+                                           grad_raw, d_vertices, (cudaStream_t)stream);
+}
+
 int pmr_shade_diffuse_forward(pmr_context *ctx, const float *pixels, const float *light_positions,
                               const float *light_intensities, const float *ambient, int B, int L, int A, int W,
                               int H, float *rgba, void *stream) {

@@ -101,6 +101,16 @@ int transform_forward_impl(Context *ctx, const float *matrices, const float *wor
 int transform_backward_impl(Context *ctx, const float *matrices, const float *d_clip, int B, int V, int shared,
                             float *d_world, cudaStream_t stream);
 
+// mesh_normals.cu
+int vertex_incidence_impl(Context *ctx, const int32_t *tris, int T, int V, int32_t *offsets, int32_t *incidence,
+                          cudaStream_t stream);
+int vertex_normals_forward_impl(Context *ctx, const float *verts, const int32_t *tris, const int32_t *offsets,
+                                const int32_t *incidence, int B, int V, float *raw, float *normals,
+                                cudaStream_t stream);
+int vertex_normals_backward_impl(Context *ctx, const float *grad_normals, const float *raw, const float *verts,
+                                 const int32_t *tris, const int32_t *offsets, const int32_t *incidence, int B, int V,
+                                 float *grad_raw, float *d_verts, cudaStream_t stream);
+
 // shade.cu
 int shade_diffuse_forward_impl(Context *ctx, const float *pixels, const float *light_positions,
                                const float *light_intensities, const float *ambient, int B, int L, int A, int W,

@@ -163,6 +163,52 @@ def transform_backward(matrices, d_clip, shared):
     return out
 
 
+def vertex_incidence(triangles, vertex_count):
+    """Topology table of the vertex-normal kernels: (offsets int32 [V+1], incidence int32 [3T])."""
+    t = _require(triangles, torch.int32, "triangles")
+    V, T = int(vertex_count), t.shape[0]
+    offsets = torch.empty((V + 1,), dtype=torch.int32, device=t.device)
+    incidence = torch.empty((3 * T,), dtype=torch.int32, device=t.device)
+    ctx = _lib.context(t.device.index)
+    with torch.cuda.device(t.device):
+        rc = _lib.load().pmr_vertex_incidence(ctx, _lib.ptr(t), T, V, _lib.ptr(offsets), _lib.ptr(incidence),
+                                              _lib.stream_ptr(t.device))
+    _lib.check(ctx, rc)
+    return offsets, incidence
+
+
+def vertex_normals_forward(vertices, triangles, offsets, incidence):
+    """vertices [B,V,3] -> (normals [B,V,3], raw un-normalised sums [B,V,3])."""
+    v = _require(vertices, torch.float32, "vertices")
+    t = _require(triangles, torch.int32, "triangles")
+    B, V, _ = v.shape
+    normals, raw = torch.empty_like(v), torch.empty_like(v)
+    ctx = _lib.context(v.device.index)
+    with torch.cuda.device(v.device):
+        rc = _lib.load().pmr_vertex_normals_forward(ctx, _lib.ptr(v), _lib.ptr(t), _lib.ptr(offsets),
+                                                    _lib.ptr(incidence), B, V, t.shape[0], _lib.ptr(raw),
+                                                    _lib.ptr(normals), _lib.stream_ptr(v.device))
+    _lib.check(ctx, rc)
+    return normals, raw
+
+
+def vertex_normals_backward(grad_normals, raw, vertices, triangles, offsets, incidence):
+    """-> d_vertices [B,V,3]."""
+    g = _require(grad_normals, torch.float32, "grad_output")
+    v = _require(vertices, torch.float32, "vertices")
+    t = _require(triangles, torch.int32, "triangles")
+    B, V, _ = v.shape
+    grad_raw, d_vertices = torch.empty_like(v), torch.empty_like(v)
+    ctx = _lib.context(v.device.index)
+    with torch.cuda.device(v.device):
+        rc = _lib.load().pmr_vertex_normals_backward(ctx, _lib.ptr(g), _lib.ptr(raw), _lib.ptr(v), _lib.ptr(t),
+                                                     _lib.ptr(offsets), _lib.ptr(incidence), B, V, t.shape[0],
+                                                     _lib.ptr(grad_raw), _lib.ptr(d_vertices),
+                                                     _lib.stream_ptr(v.device))
+    _lib.check(ctx, rc)
+    return d_vertices
+
+
 def shade_diffuse_forward(pixels, light_positions, light_intensities, ambient):
     """pixels [B,H,W,A>=9] -> RGBA [B,H,W,4] (rows flipped), diffuse + ambient Phong terms."""
     px = _require(pixels, torch.float32, "pixels")

@@ -168,6 +168,8 @@ def render(vertices, triangles, normals, diffuse_colors, camera_position, camera
         raise ValueError("Specular colors and shininess coefficients must be supplied together.")
 
     home = vertices.device
+    if home.type != "cuda" and not torch.cuda.is_available():
+        raise RuntimeError("pytorch_mesh_renderer_b200 needs a CUDA device; there is no CPU fallback")
     device = home if home.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
     to = lambda t: t.to(device) if t is not None else None
     vertices, normals, diffuse_colors = to(vertices), to(normals), to(diffuse_colors)
