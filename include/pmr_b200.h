@@ -35,6 +35,7 @@
 #ifndef PMR_B200_H_
 #define PMR_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__GNUC__)
@@ -168,6 +169,34 @@ PMR_API int pmr_transform_forward(pmr_context *ctx, const float *matrices, const
                                   int B, int V, int shared, float *clip_vertices, void *stream);
 PMR_API int pmr_transform_backward(pmr_context *ctx, const float *matrices, const float *d_clip_vertices,
                                    int B, int V, int shared, float *d_world_vertices, void *stream);
+
+/*
+ * Multi-GPU exchange of the shared-mesh gradient over peer memory (one process per GPU of
+ * one NVLink / NVSwitch box).  pmr_transform_backward_exchange is pmr_transform_backward with shared = 1 FUSED with
+ * the sum over the ranks: the kernel that reduces this rank's views stores its partial [V,3] into a slot of every
+ * peer's exchange buffer (plain stores over NVLink) and raises a flag there; a second kernel waits for the world's
+ * flags and adds the slots in rank order into d_world_vertices.  Every rank ends with the bit-identical sum over
+ * all ranks' views; there is no collective-library call and no host synchronisation in the step.
+ *
+ * Setup, once: every rank allocates an exchange buffer of pmr_peer_exchange_bytes(3 * V, world) bytes with
+ * pmr_peer_alloc (zero-filled; `handle` receives PMR_PEER_HANDLE_BYTES bytes to send to the peers by any means),
+ * opens every peer's handle with pmr_peer_open, and the ranks meet at a host barrier before the first step.
+ * peer_buffers[r] is rank r's buffer as mapped in THIS process (own allocation at [rank]).  `epoch` counts the
+ * calls on this set of buffers from 1 and must be the same number on every rank for the same step.  A rank whose
+ * peer does not deliver within ~2 s gives up waiting (pmr_peer_status reports 1) instead of hanging the device.
+ * Teardown: host barrier, pmr_peer_close on the opened pointers, pmr_peer_free on the own one.  world <= PMR_MAX_PEERS.
+ */
+#define PMR_MAX_PEERS 16
+#define PMR_PEER_HANDLE_BYTES 64
+PMR_API size_t pmr_peer_exchange_bytes(long long n_floats, int world);
+PMR_API int pmr_peer_alloc(pmr_context *ctx, size_t bytes, void **ptr, void *handle);
+PMR_API int pmr_peer_open(pmr_context *ctx, const void *handle, void **ptr);
+PMR_API int pmr_peer_close(pmr_context *ctx, void *ptr);
+PMR_API int pmr_peer_free(pmr_context *ctx, void *ptr);
+PMR_API int pmr_peer_status(pmr_context *ctx, const void *own_buffer, int *status);
+PMR_API int pmr_transform_backward_exchange(pmr_context *ctx, const float *matrices, const float *d_clip_vertices,
+                                            int B, int V, void *const *peer_buffers, int rank, int world,
+                                            long long epoch, float *d_world_vertices, void *stream);
 
 /*
  * Vertex normals of a triangle mesh (reference src/common/meshes.py:3-35 compute_vertex_normals; SURVEY.md

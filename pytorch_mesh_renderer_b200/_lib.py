@@ -42,6 +42,14 @@ _PROTOTYPES = {
                                                           _vp, _vp, _i, _vp]),
     "pmr_transform_forward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "pmr_transform_backward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "pmr_peer_exchange_bytes": (ctypes.c_size_t, [ctypes.c_longlong, _i]),
+    "pmr_peer_alloc": (ctypes.c_int, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp), _vp]),
+    "pmr_peer_open": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_vp)]),
+    "pmr_peer_close": (ctypes.c_int, [_vp, _vp]),
+    "pmr_peer_free": (ctypes.c_int, [_vp, _vp]),
+    "pmr_peer_status": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_i)]),
+    "pmr_transform_backward_exchange": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, ctypes.POINTER(_vp), _i, _i,
+                                                       ctypes.c_longlong, _vp, _vp]),
     "pmr_vertex_incidence": (ctypes.c_int, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "pmr_vertex_normals_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pmr_vertex_normals_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -12,10 +12,11 @@ class _TransformVertices(torch.autograd.Function):
     """matrices [B,4,4] x vertices ([V,3] shared by all views, or [B,V,3]) -> clip [B,V,4]."""
 
     @staticmethod
-    def forward(ctx, matrices, vertices):
+    def forward(ctx, matrices, vertices, exchange=None):
         shared = vertices.dim() == 2
         ctx.save_for_backward(matrices, vertices)
         ctx.shared = shared
+        ctx.exchange = exchange if shared else None
         return ops.transform_forward(matrices, vertices, shared)
 
     @staticmethod
@@ -23,13 +24,17 @@ class _TransformVertices(torch.autograd.Function):
         matrices, vertices = ctx.saved_tensors
         d_matrices = d_vertices = None
         if ctx.needs_input_grad[1]:
-            d_vertices = ops.transform_backward(matrices, d_clip.contiguous(), ctx.shared)
+            if ctx.exchange is not None:
+                # multi-GPU: partial over the local views + sum over the ranks through peer memory, fused
+                d_vertices = ctx.exchange.reduce(matrices, ops._aligned(d_clip.contiguous()))
+            else:
+                d_vertices = ops.transform_backward(matrices, d_clip.contiguous(), ctx.shared)
         if ctx.needs_input_grad[0]:
             # camera fitting (reference example4): d M_b = sum_v d_clip[b,v] (x) (x, y, z, 1); off the hot path
             w = vertices.unsqueeze(0).expand(matrices.shape[0], -1, -1) if ctx.shared else vertices
             hom = torch.cat([w, torch.ones_like(w[..., :1])], 2)
             d_matrices = torch.einsum("bvi,bvj->bij", d_clip, hom)
-        return d_matrices, d_vertices
+        return d_matrices, d_vertices, None
 
 
 def _on_device(*tensors):
@@ -58,13 +63,14 @@ def transform_homogeneous(matrices, vertices):
     return out.to(home) if home != dev else out
 
 
-def transform_shared_mesh(matrices, vertices):
+def transform_shared_mesh(matrices, vertices, exchange=None):
     """One mesh [V,3] seen by B views: matrices [B,4,4] -> clip [B,V,4]; the gradient with respect to
-    `vertices` comes back as [V,3], already summed over the views."""
+    `vertices` comes back as [V,3], already summed over the views -- and, with `exchange` (a
+    distributed.SharedGradientExchange), over the views of ALL ranks."""
     if len(matrices.shape) != 3 or len(vertices.shape) != 2:
         raise ValueError("expected matrices [B,4,4] and vertices [V,3]")
     dev = _on_device(matrices, vertices)
-    return _TransformVertices.apply(matrices.to(dev).float(), vertices.to(dev).float())
+    return _TransformVertices.apply(matrices.to(dev).float(), vertices.to(dev).float(), exchange)
 
 
 # ---------------------------------------------------------------------------------------------

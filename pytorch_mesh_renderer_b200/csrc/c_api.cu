@@ -385,6 +385,82 @@ int pmr_transform_backward(pmr_context *ctx, const float *matrices, const float 
                                       (cudaStream_t)stream);
 }
 
+size_t pmr_peer_exchange_bytes(long long n_floats, int world) {
+  if (n_floats < 0 || world < 1 || world > PMR_MAX_PEERS) return 0;
+  return pmr::peer_exchange_bytes(n_floats, world);
+}
+
+int pmr_peer_alloc(pmr_context *ctx, size_t bytes, void **ptr, void *handle) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (!ptr || !handle || bytes == 0) return set_error(ctx, PMR_ERR_INVALID, "null pointer or zero size");
+  static_assert(sizeof(cudaIpcMemHandle_t) == PMR_PEER_HANDLE_BYTES, "handle size");
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  void *p = nullptr;
+  PMR_CUDA(ctx, cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(handle), p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return set_error(ctx, PMR_ERR_CUDA, "peer buffer setup failed: %s", cudaGetErrorString(e));
+  }
+  *ptr = p;
+  return PMR_OK;
+}
+
+int pmr_peer_open(pmr_context *ctx, const void *handle, void **ptr) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (!ptr || !handle) return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  PMR_CUDA(ctx, cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return PMR_OK;
+}
+
+int pmr_peer_close(pmr_context *ctx, void *ptr) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (!ptr) return PMR_OK;
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  PMR_CUDA(ctx, cudaIpcCloseMemHandle(ptr));
+  return PMR_OK;
+}
+
+int pmr_peer_free(pmr_context *ctx, void *ptr) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (!ptr) return PMR_OK;
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  PMR_CUDA(ctx, cudaFree(ptr));
+  return PMR_OK;
+}
+
+int pmr_peer_status(pmr_context *ctx, const void *own_buffer, int *status) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (!own_buffer || !status) return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  PMR_CUDA(ctx, cudaMemcpy(status, static_cast<const char *>(own_buffer) + 128, sizeof(int), cudaMemcpyDeviceToHost));
+  return PMR_OK;
+}
+
+int pmr_transform_backward_exchange(pmr_context *ctx, const float *matrices, const float *d_clip_vertices, int B,
+                                    int V, void *const *peer_buffers, int rank, int world, long long epoch,
+                                    float *d_world_vertices, void *stream) {
+  if (!ctx) return PMR_ERR_INVALID;
+  if (B < 0 || V < 0) return set_error(ctx, PMR_ERR_INVALID, "negative batch/vertex count");
+  if (world < 1 || world > PMR_MAX_PEERS || rank < 0 || rank >= world)
+    return set_error(ctx, PMR_ERR_INVALID, "rank / world outside 0 <= rank < world <= PMR_MAX_PEERS");
+  if (epoch < 1) return set_error(ctx, PMR_ERR_INVALID, "epochs count from 1");
+  if (!matrices || !d_clip_vertices || !d_world_vertices || !peer_buffers)
+    return set_error(ctx, PMR_ERR_INVALID, "null pointer argument");
+  for (int r = 0; r < world; ++r)
+    if (!peer_buffers[r]) return set_error(ctx, PMR_ERR_INVALID, "null peer buffer");
+  if (!pmr::aligned16(d_clip_vertices)) return set_error(ctx, PMR_ERR_INVALID, "d_clip_vertices must be 16-byte aligned");
+  if (V == 0) return PMR_OK;
+  PMR_CUDA(ctx, cudaSetDevice(ctx->device));
+  return pmr::transform_backward_exchange_impl(ctx, matrices, d_clip_vertices, B, V, peer_buffers, rank, world, epoch,
+                                               d_world_vertices, (cudaStream_t)stream);
+}
+
 int pmr_vertex_incidence(pmr_context *ctx, const int32_t *triangles, int T, int V, int32_t *offsets,
                          int32_t *incidence, void *stream) {
   if (!ctx) return PMR_ERR_INVALID;

@@ -111,6 +111,12 @@ int vertex_normals_backward_impl(Context *ctx, const float *grad_normals, const 
                                  const int32_t *tris, const int32_t *offsets, const int32_t *incidence, int B, int V,
                                  float *grad_raw, float *d_verts, cudaStream_t stream);
 
+// peer_exchange.cu
+size_t peer_exchange_bytes(long long n_floats, int world);
+int transform_backward_exchange_impl(Context *ctx, const float *matrices, const float *d_clip, int B, int V,
+                                     void *const *peers, int rank, int world, long long epoch, float *d_world,
+                                     cudaStream_t stream);
+
 // shade.cu
 int shade_diffuse_forward_impl(Context *ctx, const float *pixels, const float *light_positions,
                                const float *light_intensities, const float *ambient, int B, int L, int A, int W,

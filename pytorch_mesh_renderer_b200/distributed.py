@@ -7,8 +7,12 @@ the gradient of parameters that all views share -- the world-space mesh in multi
 its local views' clip-space gradients to one world-space [V,3] tensor on the device (autograd of
 `transform_homogeneous` + the broadcast), then ONE all-reduce(sum) moves it over NVLink (NCCL).
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def shard_views(n_views, rank=None, world_size=None):
@@ -50,18 +54,135 @@ def all_reduce_gradients(tensors, group=None):
     return tensors
 
 
+class SharedGradientExchange:
+    """Sum of the shared-mesh gradient over the ranks through peer memory (include/pmr_b200.h
+    pmr_transform_backward_exchange, csrc/peer_exchange.cu) instead of kernel + NCCL all-reduce: the backward of
+    the vertex stage stores this rank's partial [V,3] into every peer's exchange buffer over NVLink, and a second
+    kernel adds the world's partials in rank order.  All ranks end with the bit-identical sum; the step contains
+    no collective call and no host synchronisation.
+
+    One process per GPU of one box (CUDA IPC maps the peers' buffers).  `create` returns None when the exchange
+    cannot be set up (single rank, CPU group, no peer access, more than 16 ranks): callers then all-reduce with
+    `all_reduce_gradients`.  Used by passing it to `camera_utils.transform_shared_mesh(..., exchange=ex)`, whose
+    backward then returns the COMPLETE gradient; every rank must run the same sequence of steps.
+    """
+
+    MAX_PEERS = 16
+
+    @classmethod
+    def create(cls, vertex_count, device, group=None):
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return None
+        world = dist.get_world_size(group)
+        device = torch.device(device)
+        ok = (device.type == "cuda" and world <= cls.MAX_PEERS and dist.get_backend(group) == "nccl"
+              and torch.cuda.device_count() >= world)
+        ex = None
+        if ok:
+            try:
+                ex = cls(int(vertex_count), device, group)
+            except (_lib.PmrError, ValueError):
+                ex = None
+        # all ranks or none: a rank that failed makes everybody fall back
+        votes = torch.tensor([1 if ex is not None else 0], device=device if device.type == "cuda" else "cpu")
+        dist.all_reduce(votes, op=dist.ReduceOp.MIN, group=group)
+        if int(votes.item()) == 0:
+            if ex is not None:
+                ex.close(collective=False)
+            return None
+        return ex
+
+    def __init__(self, vertex_count, device, group=None):
+        """Collective over the group.  Every rank goes through the same sequence of collectives whatever fails
+        locally (a rank that raised early would leave the others waiting); the failure is raised at the end."""
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.vertex_count = vertex_count
+        self.epoch = 0
+        self.opened = []
+        self.own = None
+        lib = _lib.load()
+        self.ctx = _lib.context(device.index)
+        failure = None
+        nbytes = lib.pmr_peer_exchange_bytes(3 * vertex_count, self.world)
+        own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            if nbytes == 0 or lib.pmr_peer_alloc(self.ctx, nbytes, ctypes.byref(own), handle) != 0:
+                failure = (lib.pmr_last_error(self.ctx) or b"exchange buffer could not be allocated").decode()
+            else:
+                self.own = own
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw if failure is None else None, group=group)
+        if failure is None and any(h is None for h in handles):
+            failure = "a peer could not allocate its exchange buffer"
+        self.peers = (ctypes.c_void_p * self.world)()
+        if failure is None:
+            for r in range(self.world):
+                if r == self.rank:
+                    self.peers[r] = own.value
+                    continue
+                p = ctypes.c_void_p()
+                with torch.cuda.device(device):
+                    rc = lib.pmr_peer_open(self.ctx, handles[r], ctypes.byref(p))
+                if rc != 0:
+                    failure = (lib.pmr_last_error(self.ctx) or b"peer buffer could not be mapped").decode()
+                    break
+                self.opened.append(p)
+                self.peers[r] = p.value
+        dist.barrier(group=group)          # every buffer is zero-filled and mapped before the first store
+        if failure is not None:
+            self.close(collective=False)
+            raise _lib.PmrError("peer exchange: " + failure)
+
+    def reduce(self, matrices, d_clip):
+        """matrices [B,4,4], d_clip [B,V,4] of this rank's views -> d_world [V,3] summed over ALL ranks' views."""
+        B, V, _ = d_clip.shape
+        assert V == self.vertex_count
+        self.epoch += 1
+        out = torch.empty((V, 3), dtype=torch.float32, device=d_clip.device)
+        with torch.cuda.device(d_clip.device):
+            rc = _lib.load().pmr_transform_backward_exchange(
+                self.ctx, _lib.ptr(matrices), _lib.ptr(d_clip), B, V, self.peers, self.rank, self.world, self.epoch,
+                _lib.ptr(out), _lib.stream_ptr(d_clip.device))
+        _lib.check(self.ctx, rc)
+        return out
+
+    def timed_out(self):
+        """True if a wait for a peer ever gave up (synchronises the device)."""
+        status = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            _lib.check(self.ctx, _lib.load().pmr_peer_status(self.ctx, self.own, ctypes.byref(status)))
+        return status.value != 0
+
+    def close(self, collective=True):
+        if self.own is None and not self.opened:
+            return
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if collective:
+                dist.barrier(group=self.group)     # nobody stores into a buffer that is about to go away
+            for p in self.opened:
+                lib.pmr_peer_close(self.ctx, p)
+            if self.own is not None:
+                lib.pmr_peer_free(self.ctx, self.own)
+        self.opened, self.own = [], None
+
+
 def rasterize_shared_mesh(world_vertices, attributes, triangles, camera_matrices, image_width, image_height,
-                          background_value):
+                          background_value, exchange=None):
     """Renders this rank's views of ONE shared mesh.
 
     world_vertices [V,3] and attributes [V,A] are shared by all views (and all ranks);
     camera_matrices [B_local,4,4] are this rank's views.  Returns the attribute images
     [B_local,H,W,A].  After `loss.backward()`, `world_vertices.grad` / `attributes.grad` hold this
-    rank's partial sums; `all_reduce_gradients([...])` completes them.
+    rank's partial sums; `all_reduce_gradients([...])` completes them.  With `exchange` (a
+    SharedGradientExchange) `world_vertices.grad` is already the sum over all ranks (attributes.grad is not).
     """
     from .camera_utils import transform_shared_mesh
     from .rasterize import rasterize_clip_space
     B = camera_matrices.shape[0]
-    clip = transform_shared_mesh(camera_matrices, world_vertices)      # one kernel; backward sums over views
+    clip = transform_shared_mesh(camera_matrices, world_vertices, exchange=exchange)   # backward sums over views
     attrs = attributes.unsqueeze(0).expand(B, -1, -1)
     return rasterize_clip_space(clip, attrs, triangles, image_width, image_height, background_value)

@@ -31,6 +31,9 @@ def _worker(rank, world, port, n_views, out):
         g = torch.Generator().manual_seed(100 + v)
         d_world += torch.randn(V, 3, generator=g)
         d_attr += torch.randn(V, A, generator=g)
+    # the peer-memory exchange is a CUDA / NCCL feature: on a CPU group every rank gets None (after the same
+    # collectives on every rank) and the caller all-reduces
+    assert D.SharedGradientExchange.create(V, torch.device("cpu")) is None
     D.all_reduce_gradients([d_world, d_attr])
     out.put((rank, list(mine), d_world.numpy(), d_attr.numpy()))
     dist.barrier()
