@@ -182,7 +182,8 @@ PMR_API int pmr_transform_backward(pmr_context *ctx, const float *matrices, cons
  * pmr_peer_alloc (zero-filled; `handle` receives PMR_PEER_HANDLE_BYTES bytes to send to the peers by any means),
  * opens every peer's handle with pmr_peer_open, and the ranks meet at a host barrier before the first step.
  * peer_buffers[r] is rank r's buffer as mapped in THIS process (own allocation at [rank]).  `epoch` counts the
- * calls on this set of buffers from 1 and must be the same number on every rank for the same step.  A rank whose
+ * calls on this set of buffers from 1 (below 2^30: PMR_ERR_SIZE after that, allocate a new set) and must be the
+ * same number on every rank for the same step.  A rank whose
  * peer does not deliver within ~2 s gives up waiting (pmr_peer_status reports 1) instead of hanging the device.
  * Teardown: host barrier, pmr_peer_close on the opened pointers, pmr_peer_free on the own one.  world <= PMR_MAX_PEERS.
  */

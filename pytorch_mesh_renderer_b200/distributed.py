@@ -137,8 +137,9 @@ class SharedGradientExchange:
     def reduce(self, matrices, d_clip):
         """matrices [B,4,4], d_clip [B,V,4] of this rank's views -> d_world [V,3] summed over ALL ranks' views."""
         B, V, _ = d_clip.shape
-        assert V == self.vertex_count
-        self.epoch += 1
+        if V != self.vertex_count:
+            raise ValueError("exchange was created for %d vertices, got %d" % (self.vertex_count, V))
+        self.epoch += 1                    # one set of buffers serves 2^30 steps (the library refuses more)
         out = torch.empty((V, 3), dtype=torch.float32, device=d_clip.device)
         with torch.cuda.device(d_clip.device):
             rc = _lib.load().pmr_transform_backward_exchange(
