@@ -198,6 +198,73 @@ def bind_near_gpu(device_index):
         return "affinity unchanged (%s)" % type(e).__name__
 
 
+def count_raster_work(clip_vertices, triangles, width, height, max_tests=60_000_000):
+    """Instrumented pass for the FP32 roofline: how many pixel visits (N_bbox, the clamped pixel boxes
+    of K.cpp:367-375) and inside-test passes (N_inside, K.cpp:380) ONE image costs the reference algorithm.
+    Host numpy over a strided sample of the triangles (at most `max_tests` pixel visits), scaled back; fp32
+    arithmetic in the reference's operation order, but only counts leave this function."""
+    import numpy as np
+    v = np.asarray(clip_vertices, np.float32)
+    t = np.asarray(triangles, np.int64)
+    T = t.shape[0]
+    if T == 0:
+        return 0, 0, 1
+    p = v[t]                                                      # [T,3,4]
+    x, y, w = p[..., 0], p[..., 1], p[..., 3]
+    alive = ~(w < 0).all(1)                                       # K.cpp:339
+    front = (w > 0).all(1)
+    half_w, half_h = np.float32(0.5 * width), np.float32(0.5 * height)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sx = (x / w + np.float32(1.0)) * half_w
+        sy = (y / w + np.float32(1.0)) * half_h
+    clampi = lambda a, hi: np.clip(np.nan_to_num(a, nan=0.0, posinf=1e9, neginf=-1e9), 0, hi).astype(np.int64)
+    left = np.where(front, clampi(np.floor(sx.min(1)), width), 0)
+    right = np.where(front, clampi(np.ceil(sx.max(1)), width), width)
+    bottom = np.where(front, clampi(np.floor(sy.min(1)), height), 0)
+    top = np.where(front, clampi(np.ceil(sy.max(1)), height), height)
+    bw = np.where(alive, np.maximum(right - left, 0), 0)
+    bh = np.where(alive, np.maximum(top - bottom, 0), 0)
+    area = bw * bh
+    total = int(area.sum())
+    stride = max(1, -(-total // max_tests))
+    pick = np.arange(0, T, stride)
+    n_bbox = int(area[pick].sum())
+    # unnormalised inverse, K.cpp:61-87 (rows are the edge functions), sign-flipped for negative determinants
+    x0, x1, x2 = x[pick, 0], x[pick, 1], x[pick, 2]
+    y0, y1, y2 = y[pick, 0], y[pick, 1], y[pick, 2]
+    w0, w1, w2 = w[pick, 0], w[pick, 1], w[pick, 2]
+    m = np.stack([y1 * w2 - w1 * y2, x2 * w1 - w2 * x1, x1 * y2 - y1 * x2,
+                  y2 * w0 - w2 * y0, x0 * w2 - w0 * x2, x2 * y0 - y2 * x0,
+                  y0 * w1 - w0 * y1, x1 * w0 - w1 * x0, x0 * y1 - y0 * x1], 1).astype(np.float32)
+    det = x0 * m[:, 0] + x1 * m[:, 3] + x2 * m[:, 6]
+    m = np.where((det < 0)[:, None], -m, m)
+    cx = ((np.arange(width, dtype=np.float64) + 0.5) / float(half_w) - 1.0).astype(np.float32)   # K.cpp:376-377
+    cy = ((np.arange(height, dtype=np.float64) + 0.5) / float(half_h) - 1.0).astype(np.float32)
+    a_s, bw_s, l_s, b_s = area[pick], bw[pick], left[pick], bottom[pick]
+    n_inside = 0
+    chunk_at, k = 0, len(pick)
+    while chunk_at < k:
+        stop = chunk_at + 1
+        tests = int(a_s[chunk_at])
+        while stop < k and tests + int(a_s[stop]) <= 4_000_000:
+            tests += int(a_s[stop])
+            stop += 1
+        if tests:
+            sel = np.arange(chunk_at, stop)
+            reps = a_s[sel]
+            tri = np.repeat(sel, reps)
+            off = np.arange(tests) - np.repeat(np.cumsum(reps) - reps, reps)
+            px = cx[np.minimum(l_s[tri] + off % np.maximum(bw_s[tri], 1), width - 1)]
+            py = cy[np.minimum(b_s[tri] + off // np.maximum(bw_s[tri], 1), height - 1)]
+            mm = m[tri]
+            e0 = mm[:, 0] * px + mm[:, 1] * py + mm[:, 2]
+            e1 = mm[:, 3] * px + mm[:, 4] * py + mm[:, 5]
+            e2 = mm[:, 6] * px + mm[:, 7] * py + mm[:, 8]
+            n_inside += int(((np.minimum(np.minimum(e0, e1), e2) >= 0) & (np.maximum(np.maximum(e0, e1), e2) > 0)).sum())
+        chunk_at = stop
+    return n_bbox * stride, n_inside * stride, stride
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -411,6 +478,34 @@ def main():
                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * secs / e2e_steps,
                "call": "pmr_rasterize_clip_space_host (C ABI, pinned host buffers in, host buffers out)",
                "host_placement": placement}
+
+    # ---- the other roofline: FP32 pipe, F = 12 N_bbox + 20 N_inside + (230 + 18 A) N_cov per step,
+    # against 148 SMs x 128 lanes x SM clock non-FMA instructions per second (the parity contract forbids FMA).
+    # N_bbox / N_inside come from an instrumented host pass over image 0 (scaled by the batch), N_cov from the
+    # device buffers of one forward call.  Diagnostic: a failure here is reported, not raised.
+    try:
+        if rank != 0:
+            raise RuntimeError("reported by rank 0 only")
+        n_bbox, n_inside, tri_stride = count_raster_work(sc["clip_vertices"][0], sc["triangles"], W, H)
+        with torch.no_grad():
+            _, (_, bary_dev, _) = pmr.rasterize_clip_space(clip, attrs, tris, W, H, bg, return_buffers=True)
+            n_cov = int((bary_dev.sum(dim=3) > 0.5).sum().item())
+            del bary_dev
+        flops = 12.0 * n_bbox * B + 20.0 * n_inside * B + (230.0 + 18.0 * A) * n_cov
+        fp32_peak = 148 * 128 * float(clocks.get("sm_max_mhz") or 1965.0) * 1e6
+        fp32_floor_ms = flops / fp32_peak * 1e3
+        hbm_floor_ms = (bytes_fwd + bytes_bwd) / (peak * 1e9) * 1e3
+        roofline["fp32"] = {
+            "flops_per_step": flops, "n_bbox_per_image": n_bbox, "n_inside_per_image": n_inside,
+            "n_covered_pixels": n_cov, "depth_complexity": n_inside * B / float(P),
+            "sample": "image 0, every %d%s triangle, scaled by the batch" % (tri_stride, "th" if tri_stride > 1 else "st"),
+            "peak": fp32_peak / 1e12, "unit": "T non-FMA fp32 instructions/s",
+            "achieved": flops / (ms_step * 1e-3) / 1e12, "frac": fp32_floor_ms / ms_step, "floor_ms": fp32_floor_ms}
+        roofline["hbm_floor_ms"] = hbm_floor_ms
+        roofline["slower_roofline"] = "fp32" if fp32_floor_ms > hbm_floor_ms else "hbm"
+        roofline["frac_of_slower_roofline"] = max(fp32_floor_ms, hbm_floor_ms) / ms_step
+    except Exception as e:                       # noqa: BLE001
+        roofline["fp32"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         line = {

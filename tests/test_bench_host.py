@@ -65,3 +65,23 @@ def test_placement_never_raises(monkeypatch):
         raise RuntimeError("no driver")
     monkeypatch.setattr(torch.cuda, "get_device_properties", boom)
     assert bench.bind_near_gpu(0).startswith("affinity unchanged")
+
+
+def test_work_counter_matches_the_oracle_counters():
+    """bench.count_raster_work (the instrumented pass behind the FP32 roofline) counts the same pixel visits and
+    inside-test passes as the oracle's forward pass, triangle for triangle, when nothing is sampled."""
+    import bench
+    from oracle import oracle
+    from pytorch_mesh_renderer_b200 import synthetic as S
+    for sc in (S.sphere_views(40, 39, 1, 128), S.occlusion_soup(1, 192, n_triangles=150), S.cube_test_scene(160, 120)):
+        cv, tr, W, H = sc["clip_vertices"][0], sc["triangles"], sc["width"], sc["height"]
+        counters = oracle.forward(cv, tr, W, H, return_counters=True)[3]
+        n_bbox, n_inside, stride = bench.count_raster_work(cv, tr, W, H)
+        assert (n_bbox, n_inside, stride) == (int(counters[0]), int(counters[1]), 1)
+    # sampled: an estimate, scaled back by the stride
+    sc = S.sphere_views(60, 59, 1, 128)
+    cv, tr = sc["clip_vertices"][0], sc["triangles"]
+    exact = bench.count_raster_work(cv, tr, 128, 128)
+    rough = bench.count_raster_work(cv, tr, 128, 128, max_tests=exact[0] // 4)
+    assert rough[2] >= 4 and abs(rough[0] - exact[0]) < 0.2 * exact[0] and abs(rough[1] - exact[1]) < 0.25 * exact[1]
+    assert bench.count_raster_work(cv, tr[:0], 128, 128) == (0, 0, 1)
