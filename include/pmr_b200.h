@@ -207,7 +207,9 @@ PMR_API int pmr_transform_backward_exchange(pmr_context *ctx, const float *matri
  * offsets int32 [V+1] and incidence int32 [3T], row v = the (corner, triangle) pairs with
  * triangles[triangle][corner] == v, coded corner << 30 | triangle and sorted ascending -- the order in which
  * the reference's three index_add_ passes (meshes.py:23-33) reach the vertex.  T < 2^30; vertex ids outside
- * [0, V) are skipped (the reference raises an index error).
+ * [0, V) are skipped (the reference raises an index error).  The rows are ordered by counting inside each row, so the
+ * build costs the SUM OF SQUARED VALENCES in comparisons (the pole of a UV sphere with 700 longitudes: nothing; one
+ * vertex shared by 10^6 triangles: minutes) -- a one-time cost per topology, sized for meshes, not for star graphs.
  *
  * pmr_vertex_normals_forward: vertices float32 [B,V,3] -> normals float32 [B,V,3] (normalised with
  * eps = 1e-6, meshes.py:34) and, when raw != NULL, the summed un-normalised normals [B,V,3] that the backward
