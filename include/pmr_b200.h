@@ -28,6 +28,8 @@
  *     enqueued on it and nothing on the device-pointer entry points waits for the device (the
  *     passes are capturable in a CUDA graph once the workspace has grown to size).  A context
  *     must not be used from two streams at once.
+ *   - Every entry point that takes a context makes the context's device the calling thread's current CUDA
+ *     device (cudaSetDevice) and leaves it so; callers that juggle several devices restore their own.
  *   - Every function returns PMR_OK (0) or a negative PMR_ERR_* code; pmr_last_error() gives the
  *     message.  There is no CPU fallback: without a CUDA device pmr_create fails.
  *   - Outputs are fully written by the callee (no pre-initialisation required).

@@ -56,6 +56,33 @@ def build(force=False, verbose=False):
     return OUT_SO
 
 
+# The reference's Python layers of the path (and what they import), staged beside the kernel so that the
+# reference arm of bench.py and the drop-in tests run the STOCK code on the GPU box, where /root/reference does
+# not exist.  Like the .so they are git-ignored: nothing of the reference enters this repository's history.
+REF_ROOT = "/root/reference"
+PY_DIR = os.path.join(OUT_DIR, "pysrc")
+PY_FILES = ["src/__init__.py", "src/common/__init__.py", "src/common/camera_utils.py", "src/common/meshes.py",
+            "src/common/obj_utils.py", "src/common/shapes.py", "src/common/debug_utils.py",
+            "src/mesh_renderer/__init__.py", "src/mesh_renderer/rasterize.py",
+            "src/mesh_renderer/rasterize_triangles_ext.py", "src/mesh_renderer/rasterize_triangles_python.py",
+            "src/mesh_renderer/render.py"]
+
+
+def stage_python(force=False):
+    """Copies the files above to oracle/_ref/pysrc/ (verbatim).  Returns the directory to put on sys.path, or
+    None when neither the reference nor an earlier staging is present."""
+    import shutil
+    if os.path.isdir(os.path.join(REF_ROOT, "src", "mesh_renderer")):
+        for rel in PY_FILES:
+            src, dst = os.path.join(REF_ROOT, rel), os.path.join(PY_DIR, rel)
+            if not os.path.exists(src):
+                continue
+            if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+                os.makedirs(os.path.dirname(dst), exist_ok=True)
+                shutil.copyfile(src, dst)
+    return PY_DIR if os.path.exists(os.path.join(PY_DIR, "src", "mesh_renderer", "rasterize.py")) else None
+
+
 def load():
     """Import the built module (torch must be imported first so libtorch is resolvable)."""
     import importlib.util
@@ -72,3 +99,4 @@ def load():
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv, verbose=True)
     print("reference kernel:", p)
+    print("reference python layers:", stage_python(force="--force" in sys.argv))

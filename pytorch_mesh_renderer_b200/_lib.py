@@ -99,7 +99,10 @@ def context(device_index):
             if not torch.cuda.is_available():
                 raise RuntimeError("pytorch_mesh_renderer_b200 needs a CUDA device; there is no CPU fallback")
             handle = _vp()
-            rc = lib.pmr_create(int(device_index), ctypes.byref(handle))
+            # pmr_create (like every entry point) makes `device_index` the calling thread's current CUDA
+            # device; the guard restores the caller's device afterwards.
+            with torch.cuda.device(int(device_index)):
+                rc = lib.pmr_create(int(device_index), ctypes.byref(handle))
             if rc != 0:
                 raise PmrError("pmr_create(device=%d) failed with code %d" % (device_index, rc))
             ctx = handle

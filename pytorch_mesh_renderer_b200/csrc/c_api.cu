@@ -5,6 +5,8 @@
 
 #include <new>
 
+#include <stdlib.h>
+
 #include "pmr_internal.cuh"
 
 struct pmr_context : public pmr::Context {};
@@ -115,6 +117,16 @@ int pmr_create(int device, pmr_context **out) {
   if (!ctx) return PMR_ERR_INVALID;
   ctx->device = device;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (const char *v = getenv("PMR_STRIP_BLOCKS")) ctx->strip_blocks_override = atoi(v);    // tuning experiments only
+  if (const char *v = getenv("PMR_NO_TMA")) ctx->no_tma = atoi(v);
+  {
+    // how long a rank waits for its peers' partial sums before it declares the exchange broken (seconds)
+    double seconds = 10.0;
+    if (const char *v = getenv("PMR_PEER_WAIT_SECONDS")) seconds = atof(v) > 0.0 ? atof(v) : seconds;
+    int khz = 1900000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    ctx->peer_wait_cycles = (long long)(seconds * 1e3 * (double)khz);
+  }
   *out = ctx;
   return PMR_OK;
 }
@@ -126,6 +138,7 @@ void pmr_destroy(pmr_context *ctx) {
   ctx->scratch.release();
   ctx->keys.release();
   ctx->centers.release();
+  ctx->staging.release();
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
   for (cudaEvent_t e : ctx->host_events) cudaEventDestroy(e);
@@ -271,10 +284,9 @@ int pmr_rasterize_clip_space_host(pmr_context *ctx, const float *vertices, const
   const bool bwd = grad_image != nullptr;
   const size_t need = up(n_v) + up(n_a) + up(n_t) + up(n_bg) + up(n_img) * (bwd ? 2 : 1) + up(n_ids) +
                       up(n_bary) + up(n_ids) + (bwd ? up(n_v) + up(n_a) : 0) + 256;
-  static thread_local pmr::Buffer staging;   // device staging area of the host entry point
-  rc = staging.reserve(ctx, need);
+  rc = ctx->staging.reserve(ctx, need);      // device staging area of the host entry point, owned by the context
   if (rc) return rc;
-  char *cur = (char *)staging.ptr;
+  char *cur = (char *)ctx->staging.ptr;
   auto take = [&](size_t n) { char *p = cur; cur += up(n); return p; };
   float *d_v = (float *)take(n_v), *d_a = (float *)take(n_a);
   int32_t *d_t = (int32_t *)take(n_t);

@@ -12,12 +12,17 @@
 //
 // Exchange buffer of a rank (pmr_peer_alloc, zero-initialised):
 //   line 0                  CTA ticket counter of the push kernel
-//   line 1                  status word (1 = a wait timed out)
+//   line 1                  status word (1 = a wait timed out; sticky) and, 64 bytes in, the local "go" word
+//                           (epoch whose partials have all arrived; written by CTA 0 of the reduction)
 //   lines 2 ..              flags[parity][peer], one 128-byte line each: last epoch peer `peer` has delivered
 //   then                    slots[parity][peer][n_pad] floats
 // Two parities alternate by epoch.  A rank can be at most one step ahead of a peer (its own reduction of step
 // k+1 needs that peer's flag k+1, raised after the peer's reduction of step k on the peer's stream), so the
 // slots of parity k & 1 are never overwritten while a peer still reads step k.
+//
+// A wait that gives up (a peer died or fell more than the limit behind: PMR_PEER_WAIT_SECONDS, default 10 s) is
+// LOUD: the status word is set and stays set, and this and every later reduction on the buffer writes NaN into
+// its output instead of a sum of stale slots; pmr_peer_status / SharedGradientExchange.close() report it.
 #include "pmr_internal.cuh"
 
 namespace pmr {
@@ -25,7 +30,7 @@ namespace pmr {
 constexpr int kLine = 128;                               // bytes per flag line
 constexpr int kHeaderLines = 2 + 2 * PMR_MAX_PEERS;
 constexpr size_t kHeaderBytes = (size_t)kHeaderLines * kLine;
-constexpr long long kWaitCycles = 4000000000ll;          // ~2 s at 1.9 GHz: a missing peer must not hang the GPU
+constexpr int kGoOffset = kLine + 64;                    // byte offset of the "go" word
 
 struct PeerTable {
   char *base[PMR_MAX_PEERS];
@@ -95,29 +100,61 @@ transform_backward_push_kernel(const float *__restrict__ matrices, const float4 
 
 // out[i] = sum over ranks r = 0 .. world-1 (in that order) of slot[parity][r][i], once every rank's flag shows
 // `epoch`.  The slots live in this GPU's memory; they were written by the peers over NVLink, so they are read past
-// L1 (ld.global.cg) after the acquiring flag load.
+// L1 (ld.global.cg) after the acquiring flag load.  Only CTA 0 polls the peers' flags (system scope); it then
+// publishes the epoch in the local "go" word, which the other CTAs of the grid wait for (device scope) -- CTA 0
+// is in the first wave of every launch, so they never wait for a CTA that cannot run.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(char *base, int world, int parity, int epoch, long long n, long long n_pad,
-                       float *__restrict__ out) {
-  if ((int)threadIdx.x < world) {
-    const int *flag = flag_of(base, parity, threadIdx.x);
+                       long long wait_cycles, float *__restrict__ out) {
+  __shared__ int failed;
+  int *status = reinterpret_cast<int *>(base + kLine);
+  int *go = reinterpret_cast<int *>(base + kGoOffset);
+  if (threadIdx.x == 0) failed = 0;
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if ((int)threadIdx.x < world) {
+      const int *flag = flag_of(base, parity, threadIdx.x);
+      const long long t0 = clock64();
+      while (load_acquire_system(flag) < epoch) {
+        if (clock64() - t0 > wait_cycles) {
+          atomicExch(status, 1);
+          break;
+        }
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();                                   // the peers' partials (acquired above) before the go word
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(go), "r"(epoch) : "memory");
+    }
+  } else if (threadIdx.x == 0) {
     const long long t0 = clock64();
-    while (load_acquire_system(flag) < epoch) {
-      if (clock64() - t0 > kWaitCycles) {
-        atomicExch(reinterpret_cast<int *>(base + kLine), 1);
+    int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(go) : "memory");
+      if (seen == epoch) break;
+      if (clock64() - t0 > 2 * wait_cycles) {
+        atomicExch(status, 1);
         break;
       }
-      __nanosleep(200);
-    }
+      __nanosleep(100);
+    } while (true);
   }
+  if (threadIdx.x == 0) failed = *reinterpret_cast<volatile int *>(status);
   __syncthreads();
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
-  const float4 *s0 = reinterpret_cast<const float4 *>(slot_of(base, parity, 0, world, n_pad));
-  float4 acc = __ldcg(s0 + i4);
-  for (int r = 1; r < world; ++r) {
-    const float4 x = __ldcg(reinterpret_cast<const float4 *>(slot_of(base, parity, r, world, n_pad)) + i4);
-    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+  float4 acc;
+  if (failed) {
+    acc.x = acc.y = acc.z = acc.w = __int_as_float(0x7fc00000);      // never a plausible gradient
+  } else {
+    const float4 *s0 = reinterpret_cast<const float4 *>(slot_of(base, parity, 0, world, n_pad));
+    acc = __ldcg(s0 + i4);
+    for (int r = 1; r < world; ++r) {
+      const float4 x = __ldcg(reinterpret_cast<const float4 *>(slot_of(base, parity, r, world, n_pad)) + i4);
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
   }
   if (i4 * 4 + 3 < n) {
     float *o = out + i4 * 4;                             // out is [V,3] floats: 4-byte alignment only
@@ -143,8 +180,8 @@ int transform_backward_exchange_impl(Context *ctx, const float *matrices, const 
   if (smem > 48 * 1024) return set_error(ctx, PMR_ERR_SIZE, "too many views for one transform_backward launch");
   transform_backward_push_kernel<<<(V + 255) / 256, 256, smem, stream>>>(
       matrices, reinterpret_cast<const float4 *>(d_clip), B, V, table, rank, world, parity, stamp, n_pad);
-  reduce_partials_kernel<<<(unsigned)((n_pad / 4 + 255) / 256), 256, 0, stream>>>(table.base[rank], world, parity,
-                                                                                  stamp, n, n_pad, d_world);
+  reduce_partials_kernel<<<(unsigned)((n_pad / 4 + 255) / 256), 256, 0, stream>>>(
+      table.base[rank], world, parity, stamp, n, n_pad, ctx->peer_wait_cycles, d_world);
   ctx->launches += 2;
   return check_launch(ctx, "transform_backward_push_kernel / reduce_partials_kernel");
 }

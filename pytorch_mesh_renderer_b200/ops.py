@@ -1,9 +1,44 @@
 """Tensor-level wrappers over the C ABI (include/pmr_b200.h): argument checks in the
 reference's terms, output allocation on the inputs' CUDA device, launch on torch's current
 stream.  No arithmetic happens in Python."""
+import os
+
 import torch
 
 from . import _lib
+
+# Range check of the triangle indices on every call (one min/max reduction and a device synchronisation):
+# off by default like the reference's native layer (K.cpp:331-337 indexes straight into the accessor); the
+# reference's Python layer raises IndexError for such input (rast.py:118-132), which this reproduces when on.
+_check_indices = os.environ.get("PMR_CHECK_INDICES", "0") not in ("", "0")
+
+
+def set_index_checks(on):
+    """Turns the per-call range check of `triangles` against [0, vertex_count) on or off (debugging aid)."""
+    global _check_indices
+    _check_indices = bool(on)
+
+
+def _check_mesh(v, t, a=None, last=4):
+    """Shapes the kernels rely on; out-of-range sizes would make them gather out of bounds (a sticky CUDA fault)."""
+    if v.dim() != 3 or v.shape[-1] != last:
+        raise ValueError("vertices must have shape [batch_size, vertex_count, %d], got %s" % (last, tuple(v.shape)))
+    if t.dim() != 2 or t.shape[1] != 3:
+        raise ValueError("triangles must have shape [triangle_count, 3], got %s" % (tuple(t.shape),))
+    if a is not None and (a.dim() != 3 or tuple(a.shape[:2]) != tuple(v.shape[:2])):
+        raise ValueError("attributes must have shape [batch_size, vertex_count, attribute_count] matching the "
+                         "vertices %s, got %s" % (tuple(v.shape[:2]), tuple(a.shape)))
+    if _check_indices and t.numel():
+        lo, hi = int(t.min()), int(t.max())
+        if lo < 0 or hi >= v.shape[1]:
+            raise IndexError("triangle vertex index out of range: [%d, %d] with %d vertices" % (lo, hi, v.shape[1]))
+
+
+def _check_buffers(i, b, B):
+    if i.dim() != 3 or i.shape[0] != B or b.dim() != 4 or tuple(b.shape) != tuple(i.shape) + (3,):
+        raise ValueError("px_triangle_ids [B,H,W] / px_barycentric_coords [B,H,W,3] do not match the batch: %s, %s"
+                         % (tuple(i.shape), tuple(b.shape)))
+
 
 _MODE_NAMES = {"atomic": _lib.BACKWARD_ATOMIC, "ordered": _lib.BACKWARD_ORDERED}
 
@@ -38,6 +73,7 @@ def rasterize_forward(vertices, triangles, image_width, image_height):
     """vertices [B,V,4] f32, triangles [T,3] i32 -> ids [B,H,W] i32, bary [B,H,W,3], z [B,H,W]."""
     v = _aligned(_require(vertices, torch.float32, "vertices"))
     t = _require(triangles, torch.int32, "triangles")
+    _check_mesh(v, t)
     B, V, _ = v.shape
     W, H = int(image_width), int(image_height)
     dev = v.device
@@ -59,7 +95,11 @@ def rasterize_backward(df_dbary, vertices, triangles, ids, bary, mode):
     g = _require(df_dbary, torch.float32, "df_dbarycentric_coords")
     i = _require(ids, torch.int32, "px_triangle_ids")
     b = _require(bary, torch.float32, "px_barycentric_coords")
+    _check_mesh(v, t)
     B, V, _ = v.shape
+    _check_buffers(i, b, B)
+    if tuple(g.shape) != tuple(b.shape):
+        raise ValueError("df_dbarycentric_coords must have the shape of the barycentric buffer %s" % (tuple(b.shape),))
     H, W = i.shape[1], i.shape[2]
     out = torch.empty((B, V, 4), dtype=torch.float32, device=v.device)
     ctx = _lib.context(v.device.index)
@@ -77,7 +117,11 @@ def interpolate_forward(attributes, triangles, ids, bary, background):
     i = _require(ids, torch.int32, "px_triangle_ids")
     b = _require(bary, torch.float32, "px_barycentric_coords")
     bg = _require(background, torch.float32, "background_value")
+    _check_mesh(a, t, last=a.shape[-1] if a.dim() == 3 else 0)
     B, V, A = a.shape
+    _check_buffers(i, b, B)
+    if bg.numel() != A:
+        raise ValueError("background_value must have %d entries" % A)
     H, W = i.shape[1], i.shape[2]
     out = torch.empty((B, H, W, A), dtype=torch.float32, device=a.device)
     ctx = _lib.context(a.device.index)
@@ -94,8 +138,11 @@ def rasterize_interpolate_forward(vertices, attributes, triangles, background, i
     a = _require(attributes, torch.float32, "attributes")
     t = _require(triangles, torch.int32, "triangles")
     bg = _require(background, torch.float32, "background_value")
+    _check_mesh(v, t, a)
     B, V, _ = v.shape
     A = a.shape[2]
+    if bg.numel() != A:
+        raise ValueError("background_value must have %d entries" % A)
     W, H = int(image_width), int(image_height)
     dev = v.device
     ids = torch.empty((B, H, W), dtype=torch.int32, device=dev)
@@ -120,7 +167,11 @@ def rasterize_interpolate_backward(grad_image, vertices, attributes, triangles, 
     t = _require(triangles, torch.int32, "triangles")
     i = _require(ids, torch.int32, "px_triangle_ids")
     b = _require(bary, torch.float32, "px_barycentric_coords")
+    _check_mesh(v, t, a)
     B, V, A = a.shape
+    _check_buffers(i, b, B)
+    if tuple(g.shape) != tuple(i.shape) + (A,):
+        raise ValueError("grad_output must have shape %s, got %s" % (tuple(i.shape) + (A,), tuple(g.shape)))
     H, W = i.shape[1], i.shape[2]
     dev = v.device
     dv = torch.empty((B, V, 4), dtype=torch.float32, device=dev) if need_vertices else None

@@ -17,28 +17,37 @@ import torch
 from . import ops
 
 _backward_mode = os.environ.get("PMR_BACKWARD_MODE", "atomic")
+_mode_explicit = "PMR_BACKWARD_MODE" in os.environ
 
 
 def set_backward_mode(mode):
     """'atomic' (throughput; fp32 sums in arbitrary order) or 'ordered' (the reference's
     summation order, bit-reproducible; see include/pmr_b200.h)."""
-    global _backward_mode
+    global _backward_mode, _mode_explicit
     ops.mode_code(mode)
     _backward_mode = mode
+    _mode_explicit = True
 
 
 def get_backward_mode():
     return _backward_mode
 
 
+def mode_was_set_explicitly():
+    """False while the mode is the built-in default (nobody called set_backward_mode, no PMR_BACKWARD_MODE)."""
+    return _mode_explicit
+
+
 @contextlib.contextmanager
 def backward_mode(mode):
-    previous = get_backward_mode()
+    global _mode_explicit
+    previous, was_explicit = get_backward_mode(), _mode_explicit
     set_backward_mode(mode)
     try:
         yield
     finally:
         set_backward_mode(previous)
+        _mode_explicit = was_explicit
 
 
 class BarycentricRasterizer(torch.autograd.Function):
