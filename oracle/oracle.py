@@ -150,8 +150,27 @@ def atomic_mode_bound(ref32, ref64, slack=8.0):
     north-star tolerance around the exactly summed value plus `slack` times the reference's own
     worst distance from it (the reference is itself only one particular fp32 order)."""
     ref_err = np.abs(np.asarray(ref32, np.float64) - ref64).max() if ref64.size else 0.0
-    scale = np.abs(ref64).max() if ref64.size else 0.0
-    return 1e-6 + 1e-5 * np.abs(ref64) + slack * ref_err + 4e-6 * scale
+    return 1e-6 + 1e-5 * np.abs(ref64) + slack * ref_err
+
+
+def tolerance_report(mine, ref32, ref64):
+    """How a gradient computed in another summation order stands against the north-star tolerance
+    1e-6 + 1e-5*|ref| itself: the fraction of entries outside it (a) against the reference's own fp32 result,
+    (b) against the exactly summed fp32 terms, and -- the context for (b) -- the reference's own fraction
+    against the same yardstick, with the largest absolute errors."""
+    mine = np.asarray(mine, np.float64)
+    ref32 = np.asarray(ref32, np.float64)
+    ref64 = np.asarray(ref64, np.float64)
+    n = max(mine.size, 1)
+    outside = lambda a, b: float((np.abs(a - b) > 1e-6 + 1e-5 * np.abs(b)).sum()) / n
+    biggest = lambda a, b: float(np.abs(a - b).max()) if a.size else 0.0
+    return {"entries": int(mine.size),
+            "outside_vs_reference_order": outside(mine, ref32),
+            "outside_vs_f64_sum": outside(mine, ref64),
+            "reference_outside_vs_f64_sum": outside(ref32, ref64),
+            "max_abs_err_vs_f64_sum": biggest(mine, ref64),
+            "reference_max_abs_err_vs_f64_sum": biggest(ref32, ref64),
+            "max_abs_value": float(np.abs(ref64).max()) if ref64.size else 0.0}
 
 
 def rasterize_clip_space(clip_space_vertices, attributes, triangles, image_width, image_height,

@@ -1,0 +1,21 @@
+#!/bin/bash
+# round 2, call K: clean backward (direct loads, quarter-aligned reducers, predicated row loads, 16-row pieces)
+set -u
+mkdir -p gpurun_out/r02k
+show() { python - "$1" "$2" <<'PY'
+import json,sys
+try:
+    d=json.load(open(sys.argv[2]))
+    print(sys.argv[1], "ms/step", round(d["ms_per_step"],4), {k:round(v,4) for k,v in d["roofline"]["stages_ms_per_step"].items() if v})
+except Exception as e:
+    print(sys.argv[1], "failed", e)
+PY
+}
+for c in c2 c3 c5 c4; do
+  timeout 600 python bench.py --config $c --no-cpu-baseline --no-e2e --no-parity --no-configs --steps 20 --warmup 5 > gpurun_out/r02k/bench_$c.json 2> gpurun_out/r02k/bench_$c.err
+  show "$c" gpurun_out/r02k/bench_$c.json
+done
+CMD="python bench.py --config c2 --no-cpu-baseline --no-e2e --no-parity --no-configs --steps 2 --warmup 3"
+$CMD > gpurun_out/r02k/plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'backward_blocks_kernel' -s 3 -c 1 -o gpurun_out/r02k/prof_bwd_clean $CMD > gpurun_out/r02k/ncu.log 2>&1
+echo "ncu rc=$?"; tail -2 gpurun_out/r02k/ncu.log

@@ -211,13 +211,12 @@ __device__ __forceinline__ void red_add_if(bool ok, float *addr, float v) {
 // four columns, and per piece ONE fire-and-forget atomic per column; the i-th atomic instruction covers
 // U consecutive words of each of the three vertices' gradient rows.
 //
-// The sums have no fixed order in this mode, so the two places where the reference's ORDER (not its
-// per-pixel arithmetic) costs instructions are relaxed: d(out)/d(bary) is an FMA chain over the
-// attributes instead of torch's blocked inner sum, and the nine quotients by |det| skip the
-// per-numerator window test of SharedDivisor (identical bits inside the window).  The per-pixel terms
-// of K.cpp:180-269 are evaluated op for op as everywhere else.
+// The per-pixel terms are the reference's bits (K.cpp:180-269 op for op; d(out)/d(bary) folded over the
+// attributes in torch's order): only the ORDER of the sums over pixels differs from the reference in this
+// mode.  The nine quotients by |det| skip the per-numerator window test of SharedDivisor (identical bits
+// inside the window, i.e. for every quotient between 1e-30 and 1e30 in magnitude).
 
-constexpr int kPieceRows = 8;
+constexpr int kPieceRows = 16;
 constexpr int kStripWarps = 4;          // warps (= block rows of 4 pixels) per CTA
 
 template <bool FUSED, int A>
@@ -229,16 +228,6 @@ struct BlockRows {
   static constexpr int SLOTS = 32 / J;               // pieces reduced side by side
   static_assert(J <= 32, "too many attribute channels for the block kernel");
 };
-
-// One row of a piece into the lane's four column sums; lanes whose piece is shorter skip it (predicated,
-// no branch: the warp runs the longest piece's row count exactly once).
-#define PMR_PIECE_ROW(k)                                                                                   \
-  asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 a, b, c, d;\n\tsetp.gt.s32 p, %5, %6;\n\t"                 \
-               "@p ld.shared.v4.f32 {a, b, c, d}, [%4+%7];\n\t"                                            \
-               "@p add.rn.f32 %0, %0, a;\n\t@p add.rn.f32 %1, %1, b;\n\t"                                  \
-               "@p add.rn.f32 %2, %2, c;\n\t@p add.rn.f32 %3, %3, d;\n\t}"                                 \
-               : "+f"(acc0), "+f"(acc1), "+f"(acc2), "+f"(acc3)                                            \
-               : "r"(q), "r"(len), "n"(k), "n"((k) * ROW4 * 16) : "memory");
 
 __device__ __forceinline__ void red_add(float *addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
@@ -264,8 +253,8 @@ struct BlockMaps {
 // SHADE (render path, A = 9): `grad` is d(RGBA) [B,H,W,4] with flipped rows; the pixel's nine interpolated
 // channels are recomputed from the corner attributes (they were never stored) and the gradient passes through
 // the diffuse + ambient lighting (shade_math.cuh) before it enters the interpolation backward.
-template <bool FUSED, int A_STATIC, bool SHADE = false>
-__global__ void __launch_bounds__(kStripWarps * 32, SHADE ? 4 : 6)
+template <bool FUSED, int A_STATIC, bool SHADE = false, int MIN_CTAS = (SHADE ? 4 : 8)>
+__global__ void __launch_bounds__(kStripWarps * 32, MIN_CTAS)
 backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
                        const float *__restrict__ grad, const float *__restrict__ verts,
                        const float *__restrict__ attrs, const int32_t *__restrict__ tris,
@@ -280,120 +269,141 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
   using R = BlockRows<FUSED, A>;
   constexpr int E = R::E, U = R::U, J = R::J, ROW4 = R::ROW4, SLOTS = R::SLOTS;
   constexpr int GC = SHADE ? 4 : (FUSED ? A : 3);    // gradient channels per pixel
-  struct __align__(128) Boxes {              // the TMA boxes of one block (each 128-byte aligned)
-    int ids[32];
-    float bary[96];
-    float grad[32 * GC];
-  };
+  // the reduction reads up to kPieceRows - 1 rows past a piece (values unused): they must stay inside the area
+  constexpr int kTail = 32 * 16 + 32 * 4 + 96 * 4 + 32 * GC * 4 + 8 + 64;
+  constexpr int kNeeded = (kPieceRows - 1) * ROW4 * 16;
   struct __align__(128) WarpArea {
     float4 rows[32 * ROW4];                  // 32 rows of ROW4 float4 slots
     int4 vids[32];                           // per row: the triangle's vertex ids
-    Boxes boxes[2];                          // block `it` lives in boxes[it & 1] while block it + 1 is fetched
-    unsigned long long ready;                // mbarrier of the fetches (one is in flight at a time)
-    unsigned short pieces[32];               // per piece: first row | rows << 8
+    int ids[32];                             // the TMA boxes of the block in flight (each 128-byte aligned)
+    float bary[96];
+    float grad[32 * GC];
+    unsigned long long ready;                // their mbarrier (one fetch is in flight at a time)
+    unsigned short pieces[32];               // per piece: first row | rows << 8 | continues the previous piece's group << 15
+    char pad[kNeeded > kTail ? kNeeded - kTail : 1];
   };
-  static_assert(offsetof(WarpArea, boxes) % 128 == 0 && sizeof(Boxes) % 128 == 0 && offsetof(Boxes, bary) % 128 == 0 &&
-                offsetof(Boxes, grad) % 128 == 0, "TMA destinations must be 128-byte aligned");
+  static_assert(offsetof(WarpArea, ids) % 128 == 0 && offsetof(WarpArea, bary) % 128 == 0 &&
+                offsetof(WarpArea, grad) % 128 == 0, "TMA destinations must be 128-byte aligned");
   __shared__ WarpArea areas[kStripWarps];
   __shared__ Lights lights;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z;
   if (SHADE) load_lights(lights, light_positions, light_intensities, ambient, b, L);     // block barrier inside
-  const int y0 = (blockIdx.y * kStripWarps + warp) * 4, xs = blockIdx.x * strip_blocks * 8;
-  if (y0 >= H || xs >= W) return;
+  const int xs = blockIdx.x * strip_blocks * 8;
+  if ((int)(blockIdx.y * kStripWarps + (threadIdx.x >> 5)) * 4 >= H || xs >= W) return;
   const int n_blocks = min(strip_blocks, (W - xs + 7) >> 3);
-  const int iy = y0 + (lane >> 3);
-  const bool row_ok = iy < H;
   const float *verts_b = verts + (size_t)b * V * 4;
   const float *attrs_b = FUSED ? attrs + (size_t)b * V * A : nullptr;
   float *dv_b = d_verts ? d_verts + (size_t)b * V * 4 : nullptr;
   float *da_b = (FUSED && d_attrs) ? d_attrs + (size_t)b * V * A : nullptr;
 
-  WarpArea &area = areas[warp];
-  const unsigned area_at = (unsigned)__cvta_generic_to_shared(&area);
-  const unsigned bar = area_at + (unsigned)offsetof(WarpArea, ready);
-
-  unsigned phase = 0;
+  // Everything that depends on the thread only (lane, warp, the warp's shared-memory area, the block row) is
+  // re-derived from an OPAQUE copy of the thread index wherever it is needed: hoisted out of the loop and kept
+  // in registers it would be spilled around the per-pixel arithmetic, and a spilled loop variable is a
+  // local-memory round trip at the top of every block.
+  struct Where {
+    int lane, warp, y0;
+    unsigned area_at;
+    WarpArea *area;
+  };
+  const unsigned tid_kept = threadIdx.x;
+  auto where = [&]() {
+    unsigned tid = tid_kept;
+    asm volatile("" : "+r"(tid));            // opaque: what is derived from it is derived here, not before the loop
+    Where w;
+    w.lane = tid & 31;
+    w.warp = tid >> 5;
+    w.y0 = (blockIdx.y * kStripWarps + w.warp) * 4;
+    w.area = &areas[w.warp];
+    w.area_at = (unsigned)__cvta_generic_to_shared(w.area);
+    return w;
+  };
+  auto fetch_block = [&](const Where &w, int it) {    // all lanes call; one elected lane issues the copies
+    if (elect_one()) {
+      const unsigned bar = w.area_at + (unsigned)offsetof(WarpArea, ready);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(128 * (4 + GC))) : "memory");
+      const int x = xs + it * 8, y = b * H + w.y0;
+      tma_load_2d(w.area_at + (unsigned)offsetof(WarpArea, ids), &maps.ids, x, y, bar);
+      tma_load_2d(w.area_at + (unsigned)offsetof(WarpArea, bary), &maps.bary, 3 * x, y, bar);
+      // the render path's gradient image is flipped: image row H-1-iy belongs to pixel row iy
+      tma_load_2d(w.area_at + (unsigned)offsetof(WarpArea, grad), &maps.grad, GC * x, SHADE ? b * H + (H - 4 - w.y0) : y, bar);
+    }
+  };
   if (use_tma) {
-    if (lane == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    const Where w = where();
+    if (w.lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(w.area_at + (unsigned)offsetof(WarpArea, ready)) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    fetch_block(w, 0);
   }
-  auto fetch_block = [&](int it) {                   // all lanes call; one elected lane issues the copies
-    if (elect_one()) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(128 * (4 + GC))) : "memory");
-      const int x = xs + it * 8, y = b * H + y0;
-      const unsigned to = area_at + (unsigned)offsetof(WarpArea, boxes) + (it & 1) * (unsigned)sizeof(Boxes);
-      tma_load_2d(to + (unsigned)offsetof(Boxes, ids), &maps.ids, x, y, bar);
-      tma_load_2d(to + (unsigned)offsetof(Boxes, bary), &maps.bary, 3 * x, y, bar);
-      // the render path's gradient image is flipped: image row H-1-iy belongs to pixel row iy
-      tma_load_2d(to + (unsigned)offsetof(Boxes, grad), &maps.grad, GC * x, SHADE ? b * H + (H - 4 - y0) : y, bar);
-    }
-  };
-  if (use_tma) fetch_block(0);
 
   for (int it = 0; it < n_blocks; ++it) {
-    // Values that depend on the lane only are re-derived per block from an opaque copy of the lane index:
-    // hoisted out of the loop they would occupy registers through the whole per-pixel arithmetic.
-    int lane_now = lane;
-    asm volatile("" : "+r"(lane_now));
-    const bool in_image = row_ok && xs + it * 8 + (lane & 7) < W;
     int id = -1;
     float bp[3] = {0.0f, 0.0f, 0.0f};
-    const Boxes &box = area.boxes[it & 1];
-    if (use_tma) {
-      unsigned done = 0;
-      while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    float g_local[SHADE ? 9 : GC];
+    {
+      const Where w = where();
+      const int lane = w.lane, iy = w.y0 + (lane >> 3), ix = xs + it * 8 + (lane & 7);
+      const bool in_image = iy < H && ix < W;
+      if (use_tma) {
+        // exactly one fetch per block: the barrier's phase is the block's parity
+        const unsigned bar = w.area_at + (unsigned)offsetof(WarpArea, ready);
+        unsigned done = 0;
+        while (!done) {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(bar), "r"((unsigned)(it & 1)) : "memory");
+        }
+        const WarpArea &area = *w.area;
+        if (in_image) {
+          id = area.ids[lane];
+          bp[0] = area.bary[3 * lane]; bp[1] = area.bary[3 * lane + 1]; bp[2] = area.bary[3 * lane + 2];
+        }
+        if constexpr (SHADE) {
+          const float4 g4 = reinterpret_cast<const float4 *>(area.grad)[(3 - (lane >> 3)) * 8 + (lane & 7)];
+          g_local[0] = g4.x; g_local[1] = g4.y; g_local[2] = g4.z;
+        } else {
+#pragma unroll
+          for (int a = 0; a < GC; ++a) g_local[a] = area.grad[lane * GC + a];
+        }
+        __syncwarp();                             // the boxes are consumed by every lane before they are refilled
+        if (it + 1 < n_blocks) fetch_block(w, it + 1);              // lands while this block is processed
+      } else if (in_image) {
+        const size_t px = ((size_t)b * H + iy) * W + ix;
+        id = ids[px];
+        bp[0] = bary[3 * px]; bp[1] = bary[3 * px + 1]; bp[2] = bary[3 * px + 2];
+        if constexpr (SHADE) {
+          const float4 g4 = reinterpret_cast<const float4 *>(grad)[((size_t)b * H + (H - 1 - iy)) * W + ix];
+          g_local[0] = g4.x; g_local[1] = g4.y; g_local[2] = g4.z;
+        } else {
+#pragma unroll
+          for (int a = 0; a < GC; ++a) g_local[a] = __ldg(grad + px * GC + a);
+        }
       }
-      phase ^= 1u;
-      if (it + 1 < n_blocks) fetch_block(it + 1);                 // into the other boxes, while this block is processed
-      if (in_image) {
-        id = box.ids[lane];
-        bp[0] = box.bary[3 * lane]; bp[1] = box.bary[3 * lane + 1]; bp[2] = box.bary[3 * lane + 2];
-      }
-    } else if (in_image) {
-      const size_t px = ((size_t)b * H + iy) * W + xs + it * 8 + (lane & 7);
-      id = ids[px];
-      bp[0] = bary[3 * px]; bp[1] = bary[3 * px + 1]; bp[2] = bary[3 * px + 2];
     }
     if (id >= 0 && !pixel_is_covered(id, bp)) id = -1;
     if (__ballot_sync(0xffffffffu, id >= 0) == 0u) continue;
 
-    // the dependent chain id -> triangle -> vertices
+    // the dependent chain id -> triangle -> vertices.  (Base pointers pass through an opaque copy for the same
+    // reason as the thread index above: hoisted out of the loop each would hold two registers throughout.)
     int vid[3] = {0, 0, 0};
     float4 pv0 = make_float4(0.f, 0.f, 0.f, 0.f), pv1 = pv0, pv2 = pv0;
+    const int32_t *tris_now = tris;
+    const float *verts_now = verts_b, *attrs_now = attrs_b;
+    asm volatile("" : "+l"(tris_now), "+l"(verts_now), "+l"(attrs_now));
     if (id >= 0) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) vid[k] = __ldg(tris + 3 * (size_t)id + k);
-      const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
+      for (int k = 0; k < 3; ++k) vid[k] = __ldg(tris_now + 3 * (size_t)id + k);
+      const float4 *v4 = reinterpret_cast<const float4 *>(verts_now);
       pv0 = __ldg(v4 + vid[0]); pv1 = __ldg(v4 + vid[1]); pv2 = __ldg(v4 + vid[2]);
-    }
-    float g_local[SHADE ? 9 : GC];
-    if (id >= 0) {                                  // the pixel's gradient row
-      if constexpr (SHADE) {
-        const float4 g4 = use_tma ? reinterpret_cast<const float4 *>(box.grad)[(3 - (lane >> 3)) * 8 + (lane & 7)]
-                                  : reinterpret_cast<const float4 *>(grad)[((size_t)b * H + (H - 1 - iy)) * W + xs + it * 8 + (lane & 7)];
-        g_local[0] = g4.x; g_local[1] = g4.y; g_local[2] = g4.z;
-      } else if (use_tma) {
-#pragma unroll
-        for (int a = 0; a < GC; ++a) g_local[a] = box.grad[lane * GC + a];
-      } else {
-        const float *g_p = grad + (((size_t)b * H + iy) * W + xs + it * 8 + (lane & 7)) * GC;
-#pragma unroll
-        for (int a = 0; a < GC; ++a) g_local[a] = __ldg(g_p + a);
-      }
     }
     if constexpr (SHADE) {
       if (id >= 0) {
         // the pixel's interpolated channels, exactly as the forward pass computed them (rast.py:118-150)
         const float alpha = coverage_alpha(bp[0], bp[1], bp[2]);
         const float one_minus = 1.0f - alpha;
-        const float *c0 = attrs_b + (size_t)vid[0] * A, *c1 = attrs_b + (size_t)vid[1] * A, *c2 = attrs_b + (size_t)vid[2] * A;
+        const float *c0 = attrs_now + (size_t)vid[0] * A, *c1 = attrs_now + (size_t)vid[1] * A, *c2 = attrs_now + (size_t)vid[2] * A;
         float px[9];
 #pragma unroll
         for (int a = 0; a < 9; ++a) {
@@ -408,6 +418,9 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
     // Group the covered lanes by triangle and give every covered lane a ROW: the rows of one triangle
     // are consecutive (groups ordered by their first lane).  Uncovered lanes get private keys, match
     // nobody and own no row.  Every kPieceRows-th lane of a group heads a piece.
+    const Where wg = where();
+    const int lane = wg.lane;
+    WarpArea &area = *wg.area;
     const unsigned peers = __match_any_sync(0xffffffffu, id >= 0 ? id : -1 - lane);
     const int leader = __ffs(peers) - 1;
     const int group_size = __popc(peers), rank = __popc(peers & ((1u << lane) - 1u));
@@ -418,28 +431,29 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
     const unsigned heads = __reduce_or_sync(0xffffffffu, head ? (1u << pos) : 0u);   // bit r: row r starts a piece
     const int n_pieces = __popc(heads);
 
+    float gb[3] = {0.0f, 0.0f, 0.0f};
     if (id >= 0) {
-      if (head) area.pieces[__popc(heads & ((1u << pos) - 1u))] = (unsigned short)(pos | (min(kPieceRows, group_size - rank) << 8));
       // d(loss)/d(bary): given, or through the interpolation (d_b_k = sum_a (g_a*alpha) * corner_k[a])
-      float gb[3];
       float *ga = g_local;                       // g_a * alpha, in place
       if (FUSED) {
         // Covered pixels have a barycentric sum ~ 1: the clamp of rast.py:145-146 is saturated and passes
         // no gradient, so the 2*d_alpha term of the reference's autograd is exactly zero here.
         const float alpha = coverage_alpha(bp[0], bp[1], bp[2]);
-        const float *c[3] = {attrs_b + (size_t)vid[0] * A, attrs_b + (size_t)vid[1] * A, attrs_b + (size_t)vid[2] * A};
 #pragma unroll
         for (int a = 0; a < A; ++a) ga[a] *= alpha;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          float acc = ga[0] * __ldg(c[k]);
-#pragma unroll
-          for (int a = 1; a < A; ++a) acc = __fmaf_rn(ga[a], __ldg(c[k] + a), acc);
-          gb[k] = acc;
+        for (int k = 0; k < 3; ++k) {              // torch's order: the per-pixel terms are the reference's bits
+          const float *ck = attrs_now + (size_t)vid[k] * A;
+          gb[k] = torch_inner_sum(A, [&](int a) { return ga[a] * __ldg(ck + a); });
         }
       } else {
         gb[0] = g_local[0]; gb[1] = g_local[1]; gb[2] = g_local[2];
       }
+    }
+    if (id >= 0) {
+      if (head) area.pieces[__popc(heads & ((1u << pos) - 1u))] =
+          (unsigned short)(pos | (min(kPieceRows, group_size - rank) << 8) | (rank > 0 ? 0x8000 : 0));
+      float *ga = g_local;
       float m[9], terms[9];
       const float det = adjugate_signed(pv0.x, pv1.x, pv2.x, pv0.y, pv1.y, pv2.y, pv0.w, pv1.w, pv2.w, m);
       vertex_terms<false>(m, fabsf(det), bp, gb, terms);
@@ -464,33 +478,76 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
     // one atomic per column.  Column e of corner k goes to d_verts[vtx_k*4 + {0,1,3}[e]] for e < 3 and to
     // d_attrs[vtx_k*A + e-3] otherwise.
     // The lane's role: piece slot, corner, columns e = u + i*U of that corner.
-    const int slot = lane_now / J, j = lane_now - slot * J;
+    const Where wr = where();
+    float *dv_now = dv_b, *da_now = da_b;
+    asm volatile("" : "+l"(dv_now), "+l"(da_now));
+    // J == 9 (A = 9): the 27 reducers are laid out so that every quarter warp reads ONE contiguous 128 bytes of a
+    // row (lanes 8s .. 8s+7: slots j = 0..7 of piece s; lanes 24, 25, 26: slot j = 8 of pieces 0, 1, 2): a 128-bit
+    // shared load then takes its minimum of four wavefronts instead of six or seven.
+    constexpr bool kQuarters = J == 9 && SLOTS == 3;
+    const int slot = kQuarters ? (wr.lane < 24 ? wr.lane >> 3 : wr.lane - 24) : wr.lane / J;
+    const int j = kQuarters ? (wr.lane < 24 ? wr.lane & 7 : 8) : wr.lane - slot * J;
+    const int next_slot_lane = kQuarters ? (wr.lane < 24 ? wr.lane + 8 : wr.lane + 1) : wr.lane + J;   // same j, slot + 1
     const int corner = min(j / U, 2), u = j - (j / U) * U;
     const bool reducer = slot < SLOTS;
-    const unsigned col_at = area_at + (reducer ? j : 0) * 16;
+    const float4 *area_rows = wr.area->rows;
     for (int t = 0; t < n_pieces; t += SLOTS) {
       const int piece = t + slot;
       const int packed = (reducer && piece < n_pieces) ? area.pieces[piece] : 0;
-      const int first = packed & 0xff, len = packed >> 8;           // len == 0: nothing to do in this round
-      const unsigned q = col_at + first * (ROW4 * 16);
+      const int first = packed & 0xff, len = (packed >> 8) & 0x7f;  // len == 0: nothing to do in this round
+      const bool continues = (packed & 0x8000) != 0;                // same triangle as the piece before
+      const float4 *q = area_rows + first * ROW4 + (reducer ? j : 0);
       const int longest = __reduce_max_sync(0xffffffffu, len);      // warp-uniform trip count
       float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-      static_assert(kPieceRows == 8, "the jump table below is written for pieces of up to 8 rows");
-      switch (longest) {                                  // straight-line code per piece length
-        case 8: PMR_PIECE_ROW(7)
-        case 7: PMR_PIECE_ROW(6)
-        case 6: PMR_PIECE_ROW(5)
-        case 5: PMR_PIECE_ROW(4)
-        case 4: PMR_PIECE_ROW(3)
-        case 3: PMR_PIECE_ROW(2)
-        case 2: PMR_PIECE_ROW(1)
-        default: PMR_PIECE_ROW(0)
+      // Two rows per step: both loads are issued before the adds, so the shared-memory latency is paid once
+      // per step.  Loads and adds are predicated on the piece's own length (written as predicated PTX: left to
+      // itself the compiler branches around them and serialises load -> add per row): the warp runs the longest
+      // piece's steps exactly once and short pieces cost no shared-memory wavefronts for rows they do not have.
+      static_assert(kPieceRows == 16, "the steps below are written for pieces of up to 16 rows");
+#define PMR_ADD_ROW(k, v)                                                                                  \
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %4, %5;\n\t@p add.rn.f32 %0, %0, %6;\n\t@p add.rn.f32 %1, %1, %7;\n\t" \
+      "@p add.rn.f32 %2, %2, %8;\n\t@p add.rn.f32 %3, %3, %9;\n\t}"                                       \
+      : "+f"(acc0), "+f"(acc1), "+f"(acc2), "+f"(acc3)                                                     \
+      : "r"(len), "n"(k), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+#define PMR_TWO_ROWS(k)                                                                   \
+  {                                                                                       \
+    float4 v0, v1;                                                                        \
+    asm("" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w));   /* any value: unused when the row is absent */ \
+    asm("" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w));                             \
+    if ((k) < len) v0 = q[(k) * ROW4];                                                    \
+    if ((k) + 1 < len) v1 = q[((k) + 1) * ROW4];                                          \
+    PMR_ADD_ROW(k, v0)                                                                    \
+    PMR_ADD_ROW((k) + 1, v1)                                                              \
+  }
+      if (longest > 8) {
+        if (longest > 14) PMR_TWO_ROWS(14)
+        if (longest > 12) PMR_TWO_ROWS(12)
+        if (longest > 10) PMR_TWO_ROWS(10)
+        PMR_TWO_ROWS(8)
       }
-      if (len > 0) {
+      if (longest > 6) PMR_TWO_ROWS(6)
+      if (longest > 4) PMR_TWO_ROWS(4)
+      if (longest > 2) PMR_TWO_ROWS(2)
+      PMR_TWO_ROWS(0)
+#undef PMR_TWO_ROWS
+#undef PMR_ADD_ROW
+      // A triangle with more than kPieceRows pixels in the block was cut into several pieces: the sums of the
+      // pieces that share this round are added up (highest slot first) so that the triangle costs one set of
+      // atomics, not one per piece -- what matters when few vertices take all the traffic (large triangles).
+      const unsigned merging = __ballot_sync(0xffffffffu, continues && slot > 0 && len > 0);
+      if (merging) {
+#pragma unroll
+        for (int sl = SLOTS - 1; sl >= 1; --sl) {
+          const float x0 = __shfl_sync(0xffffffffu, acc0, next_slot_lane), x1 = __shfl_sync(0xffffffffu, acc1, next_slot_lane);
+          const float x2 = __shfl_sync(0xffffffffu, acc2, next_slot_lane), x3 = __shfl_sync(0xffffffffu, acc3, next_slot_lane);
+          if (slot == sl - 1 && ((merging >> (kQuarters ? sl * 8 : sl * J)) & 1u)) { acc0 += x0; acc1 += x1; acc2 += x2; acc3 += x3; }
+        }
+      }
+      if (len > 0 && !(continues && slot > 0)) {
         const int vtx = reinterpret_cast<const int *>(area.vids + first)[corner];
         const float sums[4] = {acc0, acc1, acc2, acc3};
-        float *to_vert = dv_b + (unsigned)(vtx * 4 + column_of(u < 3 ? u : 0));   // column u of the vertex row
-        float *to_attr = da_b + (unsigned)(vtx * A + u) - 3;                        // column u of the attribute row
+        float *to_vert = dv_now + (unsigned)(vtx * 4 + column_of(u < 3 ? u : 0));   // column u of the vertex row
+        float *to_attr = da_now + (unsigned)(vtx * A + u) - 3;                        // column u of the attribute row
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i * U >= E) continue;                             // beyond the last column for every lane
@@ -499,9 +556,9 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
           const bool exists = ((i + 1) * U <= E) ? true : e < E;
           if (is_vert) {
             // U < 3: columns x, y of i = 0 and w (or an attribute) of i = 1 ...: the row is walked in steps of U
-            if (dv_b != nullptr) red_add(i == 0 ? to_vert : dv_b + (unsigned)(vtx * 4 + column_of(e)), sums[i]);
+            if (dv_now != nullptr) red_add(i == 0 ? to_vert : dv_now + (unsigned)(vtx * 4 + column_of(e)), sums[i]);
           } else if (exists) {
-            if (da_b != nullptr) red_add(to_attr + i * U, sums[i]);
+            if (da_now != nullptr) red_add(to_attr + i * U, sums[i]);
           }
         }
       }
@@ -509,133 +566,340 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
     __syncwarp();                                   // rows, pieces and vertex ids are rewritten by the next block
   }
 }
-#undef PMR_PIECE_ROW
 
 // ---------------------------------------------------------------------------------------------
-// Ordered (parity) mode
+// Ordered (parity) mode: sort by vertex, fold in pixel order
 // ---------------------------------------------------------------------------------------------
+//
+// The reference adds a pixel's contributions to its triangle's three vertices in row-major pixel order, corner
+// 0..2 within a pixel, in fp32 (K.cpp:156-157, :232-269; the same order for d(attributes) through index_put_,
+// rast.py:130-132 with one torch thread).  Per image that is a list of 3*H*W ENTRIES, entry e = 3*pixel + corner
+// with key = the corner's vertex id (V for pixels that draw nothing), already in the order in which each
+// vertex must receive its terms.  A STABLE sort of the entries by key therefore lays every vertex's terms out
+// consecutively and in the reference's order:
+//   1. least-significant-digit radix sort, 8 bits (or fewer) per pass, one warp per tile of kSortTile entries:
+//      a counting kernel (per-tile digit histogram), an exclusive scan over (digit, tile) per image, and a
+//      scatter kernel in which a warp walks its tile 32 entries at a time -- rank among equal digits of the
+//      chunk by match.any, running per-digit offsets in shared memory -- so that equal keys keep their order.
+//      The first pass reads its keys straight from the id / triangle buffers; nothing is staged for it.
+//   2. segment bounds per (image, vertex) from the places where the sorted key changes;
+//   3. one warp per (image, vertex) walks its segment 32 entries at a time: the lanes evaluate the entries'
+//      terms in parallel (same per-pixel arithmetic as everywhere), park them in shared memory, and lane c folds
+//      component c over the rows strictly in order.
+// Cost is linear in the number of pixels for any mesh (the box-walking kernel this replaced was quadratic in
+// the triangle size) and every load of the fold is a gather of a few neighbouring pixels.
 
-__global__ void __launch_bounds__(256)
-vertex_box_init_kernel(int4 *__restrict__ vbox, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) vbox[i] = make_int4(INT_MAX, INT_MIN, INT_MAX, INT_MIN);   // left right bottom top
+constexpr int kSortTile = 2048;            // entries per warp and pass
+constexpr int kSortWarps = 4;              // warps per CTA (independent)
+constexpr int kSortBins = 256;
+
+// key of entry e of image b, from the forward buffers (first pass) or from the previous pass
+struct EntrySource {
+  const uint2 *sorted;                     // {key, payload} of the previous pass, or nullptr: generate
+  const int32_t *ids, *tris;
+  const float *bary;
+  int V;
+};
+
+__device__ __forceinline__ uint2 load_entry(const EntrySource &src, size_t image_entries, int b, unsigned e,
+                                            size_t pixels_per_image) {
+  if (src.sorted != nullptr) return src.sorted[(size_t)b * image_entries + e];
+  const unsigned pixel = e / 3u, corner = e - 3u * pixel;
+  const size_t p = (size_t)b * pixels_per_image + pixel;
+  const int id = src.ids[p];
+  bool covered = true;
+  if (id == 0) {                           // K.cpp:162: id 0 with barycentrics summing below 0.9 draws nothing
+    const float *bp = src.bary + 3 * p;
+    covered = !(bp[0] + bp[1] + bp[2] < kDegenerateBarySum);
+  }
+  const unsigned key = covered ? (unsigned)__ldg(src.tris + 3 * (size_t)id + corner) : (unsigned)src.V;
+  return make_uint2(key, e);
 }
 
-// Union, per (image, vertex), of the pixel boxes of the triangles that use the vertex.  A pixel
-// drawn from triangle t always lies inside t's box (K.cpp:374-375), so the union bounds every
-// pixel that can contribute to the vertex.
-__global__ void __launch_bounds__(256)
-vertex_box_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int T,
-                  int W, int H, float half_w, float half_h, int4 *__restrict__ vbox) {
-  const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  const int i0 = __ldg(tris + 3 * (size_t)t), i1 = __ldg(tris + 3 * (size_t)t + 1), i2 = __ldg(tris + 3 * (size_t)t + 2);
-  const float4 *v4 = reinterpret_cast<const float4 *>(verts + (size_t)b * V * 4);
-  const PixelBox bx = triangle_box(__ldg(v4 + i0), __ldg(v4 + i1), __ldg(v4 + i2), half_w, half_h, W, H);
-  if (bx.left >= bx.right || bx.bottom >= bx.top) return;
-  const int vid[3] = {i0, i1, i2};
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    int *q = reinterpret_cast<int *>(vbox + (size_t)b * V + vid[j]);
-    atomicMin(q + 0, bx.left);
-    atomicMax(q + 1, bx.right);
-    atomicMin(q + 2, bx.bottom);
-    atomicMax(q + 3, bx.top);
+// counts[b][digit][tile]: how many entries of the tile have this digit
+__global__ void __launch_bounds__(kSortWarps * 32)
+sort_count_kernel(EntrySource src, unsigned entries, size_t pixels_per_image, int tiles, int shift, unsigned mask,
+                  unsigned *__restrict__ counts) {
+  __shared__ unsigned hist_all[kSortWarps][kSortBins];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * kSortWarps + warp, b = blockIdx.y;
+  unsigned *hist = hist_all[warp];
+  for (int i = lane; i < kSortBins; i += 32) hist[i] = 0u;
+  __syncwarp();
+  if (tile < tiles) {
+    const unsigned begin = (unsigned)tile * kSortTile, end = min(begin + (unsigned)kSortTile, entries);
+    for (unsigned e0 = begin; e0 < end; e0 += 32) {
+      const unsigned e = e0 + lane;
+      const bool live = e < end;
+      const unsigned digit = live ? (load_entry(src, entries, b, e, pixels_per_image).x >> shift) & mask : 0xffffffffu - lane;
+      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      if (live && lane == __ffs(peers) - 1) hist[digit] += __popc(peers);
+      __syncwarp();
+    }
+    for (int i = lane; i < kSortBins; i += 32) counts[((size_t)b * kSortBins + i) * tiles + tile] = hist[i];
   }
 }
 
-constexpr int kOrderedWarps = 8;
+// exclusive prefix sum of counts[b][:] (digit-major, then tile): one CTA per image
+__global__ void __launch_bounds__(1024)
+sort_scan_kernel(unsigned *__restrict__ counts, int n) {
+  __shared__ unsigned warp_sums[32];
+  __shared__ unsigned carry;
+  unsigned *c = counts + (size_t)blockIdx.x * n;
+  if (threadIdx.x == 0) carry = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024 * 4) {
+    const int i0 = base + threadIdx.x * 4;
+    unsigned v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = i0 + k < n ? c[i0 + k] : 0u;
+    const unsigned mine = v[0] + v[1] + v[2] + v[3];
+    unsigned incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += up;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = warp_sums[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += up;
+      }
+      warp_sums[lane] = wi - w;                       // exclusive over the warps
+    }
+    __syncthreads();
+    unsigned at = carry + warp_sums[warp] + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < n) c[i0 + k] = at;
+      at += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = at;             // the last thread holds the running total
+    __syncthreads();
+  }
+}
 
-template <bool FUSED>
-__global__ void __launch_bounds__(kOrderedWarps * 32)
-backward_ordered_kernel(const float *__restrict__ grad, const float *__restrict__ verts,
-                        const float *__restrict__ attrs, const int32_t *__restrict__ tris,
-                        const int32_t *__restrict__ ids, const float *__restrict__ bary,
-                        const int4 *__restrict__ vbox, int V, int A, int W, int H, long long n_pairs,
-                        float *__restrict__ d_verts, float *__restrict__ d_attrs) {
-  extern __shared__ float rows_all[];   // [warp][lane][corner][3 + A]
+__global__ void __launch_bounds__(kSortWarps * 32)
+sort_scatter_kernel(EntrySource src, unsigned entries, size_t pixels_per_image, int tiles, int shift, unsigned mask,
+                    const unsigned *__restrict__ offsets, uint2 *__restrict__ out) {
+  __shared__ unsigned next_all[kSortWarps][kSortBins];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long pair = (long long)blockIdx.x * kOrderedWarps + warp;
-  if (pair >= n_pairs) return;
-  const int b = (int)(pair / V), v = (int)(pair % V);
+  const int tile = blockIdx.x * kSortWarps + warp, b = blockIdx.y;
+  if (tile >= tiles) return;
+  unsigned *next = next_all[warp];
+  for (int i = lane; i < kSortBins; i += 32) next[i] = offsets[((size_t)b * kSortBins + i) * tiles + tile];
+  __syncwarp();
+  uint2 *out_b = out + (size_t)b * entries;
+  const unsigned begin = (unsigned)tile * kSortTile, end = min(begin + (unsigned)kSortTile, entries);
+  for (unsigned e0 = begin; e0 < end; e0 += 32) {
+    const unsigned e = e0 + lane;
+    const bool live = e < end;
+    uint2 entry = make_uint2(0u, 0u);
+    if (live) entry = load_entry(src, entries, b, e, pixels_per_image);
+    const unsigned digit = live ? (entry.x >> shift) & mask : 0xffffffffu - lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    const unsigned before = __popc(peers & ((1u << lane) - 1u));      // equal digits in lower lanes: stable
+    unsigned at = 0u;
+    if (live) at = next[digit] + before;
+    __syncwarp();
+    if (live) {
+      out_b[at] = entry;
+      if (lane == __ffs(peers) - 1) next[digit] += __popc(peers);
+    }
+    __syncwarp();
+  }
+}
+
+// bounds[b][v] = {first, last + 1} of vertex v's run in the sorted entries of image b (zeros: no entry)
+__global__ void __launch_bounds__(256)
+segment_bounds_kernel(const uint2 *__restrict__ sorted, unsigned entries, int V, uint2 *__restrict__ bounds) {
+  const int b = blockIdx.y;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= entries) return;
+  const uint2 *s = sorted + (size_t)b * entries;
+  const unsigned key = s[i].x;
+  const unsigned prev = i > 0 ? s[i - 1].x : 0xffffffffu;
+  if (key != prev) {
+    unsigned *bb = reinterpret_cast<unsigned *>(bounds + (size_t)b * (V + 1));
+    bb[2 * key] = i;
+    if (i > 0) bb[2 * prev + 1] = i;
+  }
+  if (i == entries - 1) reinterpret_cast<unsigned *>(bounds + (size_t)b * (V + 1))[2 * key + 1] = entries;
+}
+
+constexpr int kFoldWarps = 4;
+
+// The terms ONE entry (pixel, corner j) adds to its vertex: the three vertex terms of corner j and, fused, the
+// A products (g_a*alpha)*b_j -- the same expressions as vertex_terms() / the interpolation backward evaluate
+// for all three corners, restricted to the corner that is asked for (same operations, same bits).
+template <bool FUSED, int A_STATIC>
+__device__ __forceinline__ void entry_terms(const float *__restrict__ verts_b, const float *__restrict__ attrs_b,
+                                            const int32_t *__restrict__ tris, int id, const float bp[3],
+                                            const float *__restrict__ g_p, int A_dyn, int j, float *row) {
+  const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
+  int vid[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) vid[k] = __ldg(tris + 3 * (size_t)id + k);
+  const float4 *v4 = reinterpret_cast<const float4 *>(verts_b);
+  const float4 p0 = __ldg(v4 + vid[0]), p1 = __ldg(v4 + vid[1]), p2 = __ldg(v4 + vid[2]);
+  const float bj = j == 0 ? bp[0] : (j == 1 ? bp[1] : bp[2]);
+  float g[3];
+  if (FUSED) {
+    const float alpha = coverage_alpha(bp[0], bp[1], bp[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float *ck = attrs_b + (size_t)vid[k] * A;
+      g[k] = torch_inner_sum(A, [&](int a) { return (__ldg(g_p + a) * alpha) * __ldg(ck + a); });
+    }
+    if (A_STATIC > 0) {
+#pragma unroll
+      for (int a = 0; a < (A_STATIC > 0 ? A_STATIC : 1); ++a) row[3 + a] = (__ldg(g_p + a) * alpha) * bj;
+    } else {
+      for (int a = 0; a < A; ++a) row[3 + a] = (__ldg(g_p + a) * alpha) * bj;
+    }
+  } else {
+    g[0] = g_p[0]; g[1] = g_p[1]; g[2] = g_p[2];
+  }
+  float m[9];
+  const float det = adjugate_signed(p0.x, p1.x, p2.x, p0.y, p1.y, p2.y, p0.w, p1.w, p2.w, m);
+  const SharedDivisor by_det(fabsf(det));
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {                      // K.cpp:187-269 for corner j
+    const float sc = m[c] + m[3 + c] + m[6 + c];
+    const float d0 = (-m[0 + c]) * bj + sc * bp[0] * bj;
+    const float d1 = (-m[3 + c]) * bj + sc * bp[1] * bj;
+    const float d2 = (-m[6 + c]) * bj + sc * bp[2] * bj;
+    row[c] = by_det.divide(g[0] * d0 + g[1] * d1 + g[2] * d2);
+  }
+}
+
+// One warp folds the entries of `vpw` consecutive vertices of one image (their runs are consecutive in the
+// sorted list): 32 entries at a time, lanes evaluate the entries' terms into shared-memory rows, then lane c
+// adds component c row by row IN ORDER, writing a vertex's sums out when the key changes.
+template <bool FUSED, int A_STATIC>
+__global__ void __launch_bounds__(kFoldWarps * 32)
+backward_fold_kernel(const float *__restrict__ grad, const float *__restrict__ verts,
+                     const float *__restrict__ attrs, const int32_t *__restrict__ tris,
+                     const int32_t *__restrict__ ids, const float *__restrict__ bary,
+                     const uint2 *__restrict__ sorted, const uint2 *__restrict__ bounds, unsigned entries,
+                     int V, int A_dyn, size_t pixels_per_image, int vpw, int groups_per_image,
+                     float *__restrict__ d_verts, float *__restrict__ d_attrs) {
+  extern __shared__ float fold_smem[];   // [warp]: 32 rows of ncomp floats, then 32 keys
+  const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = blockIdx.x * kFoldWarps + warp, b = blockIdx.y;
+  if (group >= groups_per_image) return;
   const int ncomp = 3 + (FUSED ? A : 0);
-  float *rows = rows_all + (size_t)warp * 32 * 3 * ncomp;
-  const int4 box = vbox[pair];
+  float *rows = fold_smem + (size_t)warp * (32 * ncomp + 32);
+  unsigned *row_keys = reinterpret_cast<unsigned *>(rows + 32 * ncomp);
+  const int v_first = group * vpw, v_count = min(vpw, V - v_first);
   const float *verts_b = verts + (size_t)b * V * 4;
   const float *attrs_b = FUSED ? attrs + (size_t)b * V * A : nullptr;
+  const uint2 *sorted_b = sorted + (size_t)b * entries;
+  float *dv_b = d_verts ? d_verts + (size_t)b * V * 4 : nullptr;
+  float *da_b = (FUSED && d_attrs) ? d_attrs + (size_t)b * V * A : nullptr;
 
-  constexpr int kMaxSlots = 4;          // components lane, lane+32, ... (A <= 125)
-  float acc[kMaxSlots] = {0.0f, 0.0f, 0.0f, 0.0f};
+  // the stream of this warp: from the first present vertex's run to the last one's (vpw <= 32)
+  uint2 mine = make_uint2(0u, 0u);
+  if (lane < v_count) mine = bounds[(size_t)b * (V + 1) + v_first + lane];
+  const bool present = mine.y > mine.x;
+  const unsigned begin = __reduce_min_sync(0xffffffffu, present ? mine.x : 0xffffffffu);
+  const unsigned end = __reduce_max_sync(0xffffffffu, present ? mine.y : 0u);
+  // vertices without entries: zero gradient
+  if (lane < v_count && !present) {
+    const int v = v_first + lane;
+    if (dv_b) *reinterpret_cast<float4 *>(dv_b + (size_t)v * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (da_b) for (int a = 0; a < A; ++a) da_b[(size_t)v * A + a] = 0.0f;
+  }
+  if (begin >= end) return;
 
-  const int bw = box.y - box.x;
-  const long long n = (box.x < box.y && box.z < box.w) ? (long long)bw * (box.w - box.z) : 0;
-  for (long long k0 = 0; k0 < n; k0 += 32) {
-    const long long k = k0 + lane;
-    int id = -1, corners = 0;
-    long long p = 0;
-    float bp[3];
-    if (k < n) {
-      const int iy = box.z + (int)(k / bw), ix = box.x + (int)(k % bw);
-      p = ((long long)b * H + iy) * W + ix;
-      id = ids[p];
-      bp[0] = bary[3 * p]; bp[1] = bary[3 * p + 1]; bp[2] = bary[3 * p + 2];
-      if (pixel_is_covered(id, bp)) {
+  constexpr int kMaxSlots = 3;          // components lane, lane + 32, lane + 64 (A <= 93)
+  float acc[kMaxSlots] = {0.0f, 0.0f, 0.0f};
+  unsigned current = 0xffffffffu;       // vertex whose sums are in acc
+  auto flush = [&](unsigned v) {
+    if (dv_b != nullptr) {
+      if (lane < 3) dv_b[(size_t)v * 4 + column_of(lane)] = acc[0];
+      if (lane == 3) dv_b[(size_t)v * 4 + 2] = 0.0f;       // z column never receives gradient
+    }
+    if (da_b != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) corners |= (__ldg(tris + 3 * (size_t)id + j) == v) << j;
+      for (int s2 = 0; s2 < kMaxSlots; ++s2) {
+        const int c = lane + 32 * s2;
+        if (c >= 3 && c < ncomp) da_b[(size_t)v * A + c - 3] = acc[s2];
       }
     }
-    const unsigned hits = __ballot_sync(0xffffffffu, corners != 0);
-    if (hits == 0u) continue;
-    if (corners != 0) {
-      PixelGrad pg;
-      const float *g_p = grad + (size_t)p * (FUSED ? A : 3);
-      pixel_grad<FUSED>(verts_b, attrs_b, tris, id, bp, g_p, A, pg);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        if (corners & (1 << j)) {
-          float *row = rows + ((size_t)lane * 3 + j) * ncomp;
-          row[0] = pg.terms[3 * j + 0]; row[1] = pg.terms[3 * j + 1]; row[2] = pg.terms[3 * j + 2];
-          if (FUSED)
-            for (int a = 0; a < A; ++a) row[3 + a] = (g_p[a] * pg.alpha) * pg.b[j];
-        }
-      }
+    for (int s2 = 0; s2 < kMaxSlots; ++s2) acc[s2] = 0.0f;
+  };
+  // Software pipeline over the chunks of 32 entries: an entry leads to its pixel, the pixel to its triangle, the
+  // triangle to its vertices -- four dependent loads.  The entry of chunk c+2 and the pixel data (id,
+  // barycentrics) of chunk c+1 are in flight while chunk c is evaluated, so two links of the chain are hidden.
+  auto load_entry_at = [&](unsigned k) { return k < end ? sorted_b[k] : make_uint2(0xffffffffu, 0u); };
+  struct PixelHead { int id; float b0, b1, b2; };
+  auto load_pixel_head = [&](const uint2 &entry) {
+    PixelHead h = {0, 0.0f, 0.0f, 0.0f};
+    if (entry.x != 0xffffffffu) {
+      const size_t p = (size_t)b * pixels_per_image + entry.y / 3u;
+      h.id = ids[p];
+      h.b0 = bary[3 * p]; h.b1 = bary[3 * p + 1]; h.b2 = bary[3 * p + 2];
     }
+    return h;
+  };
+  uint2 entry0 = load_entry_at(begin + lane), entry1 = load_entry_at(begin + 32 + lane);
+  PixelHead head0 = load_pixel_head(entry0);
+  for (unsigned k0 = begin; k0 < end; k0 += 32) {
+    const int count = (int)min(32u, end - k0);
+    const uint2 entry2 = load_entry_at(k0 + 64 + lane);
+    const PixelHead head1 = load_pixel_head(entry1);
+    if (entry0.x != 0xffffffffu) {
+      const unsigned pixel = entry0.y / 3u;
+      const int corner = (int)(entry0.y - 3u * pixel);
+      const size_t p = (size_t)b * pixels_per_image + pixel;
+      const float bp[3] = {head0.b0, head0.b1, head0.b2};
+      entry_terms<FUSED, A_STATIC>(verts_b, attrs_b, tris, head0.id, bp, grad + p * (FUSED ? A : 3), A, corner,
+                                   rows + (size_t)lane * ncomp);
+      row_keys[lane] = entry0.x;
+    }
+    entry0 = entry1; entry1 = entry2; head0 = head1;
     __syncwarp();
-    // Fold in pixel order (ascending lane), corner order within a pixel.
-    unsigned todo = hits;
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int cm = __shfl_sync(0xffffffffu, corners, src);
+    // fold strictly in entry order; the rows of one vertex within the chunk are fetched eight at a time so
+    // that only the adds are serial
+    int r = 0;
+    while (r < count) {
+      const unsigned key = row_keys[r];
+      if (key != current) {
+        if (current != 0xffffffffu) flush(current);
+        current = key;
+      }
+      int run = 1;                       // rows r .. r+run-1 share the key (warp-uniform)
+      while (r + run < count && row_keys[r + run] == key) ++run;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        if (cm & (1 << j)) {
-          const float *row = rows + ((size_t)src * 3 + j) * ncomp;
+      for (int s2 = 0; s2 < kMaxSlots; ++s2) {
+        const int c = lane + 32 * s2;
+        if (c < ncomp) {
+          const float *col = rows + (size_t)r * ncomp + c;
+          int i = 0;
+          for (; i + 8 <= run; i += 8) {
+            float t[8];
 #pragma unroll
-          for (int s = 0; s < kMaxSlots; ++s) {
-            const int c = lane + 32 * s;
-            if (c < ncomp) acc[s] += row[c];
+            for (int u = 0; u < 8; ++u) t[u] = col[(size_t)(i + u) * ncomp];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[s2] += t[u];
           }
+          for (; i < run; ++i) acc[s2] += col[(size_t)i * ncomp];
         }
       }
+      r += run;
     }
     __syncwarp();
   }
-
-  if (d_verts != nullptr) {
-    float *dv = d_verts + (size_t)pair * 4;
-    if (lane < 3) dv[column_of(lane)] = acc[0];
-    if (lane == 3) dv[2] = 0.0f;        // z column never receives gradient
-  }
-  if (FUSED && d_attrs != nullptr) {
-    float *da = d_attrs + (size_t)pair * A;
-#pragma unroll
-    for (int s = 0; s < kMaxSlots; ++s) {
-      const int c = lane + 32 * s;
-      if (c >= 3 && c < ncomp) da[c - 3] = acc[s];
-    }
-  }
+  if (current != 0xffffffffu) flush(current);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -739,13 +1003,13 @@ int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, 
     const int use_tma = make_block_maps(ctx, &maps, ids, bary, grad, fused ? A : 3, B, W, H);
 #define PMR_BLOCKS(F, AS)                                                                                 \
   backward_blocks_kernel<F, AS><<<strip_grid(W, H, B, strip), kStripWarps * 32, 0, stream>>>(            \
-      maps, use_tma, grad, verts, attrs, tris, ids, bary, V, W, H, strip, d_verts, d_attrs)
-    if (!fused) PMR_BLOCKS(false, 1);
-    else if (A == 9) PMR_BLOCKS(true, 9);
-    else if (A == 3) PMR_BLOCKS(true, 3);
-    else if (A == 4) PMR_BLOCKS(true, 4);
-    else if (A == 12) PMR_BLOCKS(true, 12);
-    else if (A == 13) PMR_BLOCKS(true, 13);
+      maps, use_tma, grad, verts, attrs, tris, ids, bary, V, W, H, strip, d_verts, d_attrs);
+    if (!fused) PMR_BLOCKS(false, 1)
+    else if (A == 9) PMR_BLOCKS(true, 9)
+    else if (A == 3) PMR_BLOCKS(true, 3)
+    else if (A == 4) PMR_BLOCKS(true, 4)
+    else if (A == 12) PMR_BLOCKS(true, 12)
+    else if (A == 13) PMR_BLOCKS(true, 13)
     else {
       // other attribute counts: one thread per pixel, per-lane atomics
       const unsigned grid = (unsigned)((total + 255) / 256);
@@ -758,31 +1022,67 @@ int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, 
   }
 
   if (mode != PMR_BACKWARD_ORDERED) return set_error(ctx, PMR_ERR_INVALID, "unknown backward mode %d", mode);
-  // shared memory of the ordered kernel: kOrderedWarps * 32 * 3 * (3 + A) floats <= 227 KB
-  if (fused && A > 72) return set_error(ctx, PMR_ERR_SIZE, "ordered backward supports at most 72 attributes");
-  int rc = ctx->scratch.reserve(ctx, (size_t)n_pairs * sizeof(int4));
+  if (fused && A > 93) return set_error(ctx, PMR_ERR_SIZE, "ordered backward supports at most 93 attributes");
+  if (total == 0 || T == 0) {
+    if (d_verts) PMR_CUDA(ctx, cudaMemsetAsync(d_verts, 0, (size_t)n_pairs * 4 * sizeof(float), stream));
+    if (fused && d_attrs) PMR_CUDA(ctx, cudaMemsetAsync(d_attrs, 0, (size_t)n_pairs * A * sizeof(float), stream));
+    return PMR_OK;
+  }
+  if (3 * ppi >= (1LL << 32)) return set_error(ctx, PMR_ERR_SIZE, "ordered backward: image too large (3*H*W must fit 32 bits)");
+  const unsigned entries = (unsigned)(3 * ppi);
+  const int tiles = (int)((entries + kSortTile - 1) / kSortTile);
+  int key_bits = 1;
+  while ((1LL << key_bits) <= (long long)V) ++key_bits;           // keys are 0 .. V
+  const int passes = (key_bits + 7) / 8;
+  const int digit_bits = (key_bits + passes - 1) / passes;
+  // workspace: two entry buffers, the per-tile digit counters, the segment bounds
+  const size_t entry_bytes = (((size_t)B * entries * sizeof(uint2)) + 255) & ~(size_t)255;
+  const size_t count_bytes = (((size_t)B * kSortBins * tiles * sizeof(unsigned)) + 255) & ~(size_t)255;
+  const size_t bound_bytes = (size_t)B * (V + 1) * sizeof(uint2);
+  int rc = ctx->scratch.reserve(ctx, 2 * entry_bytes + count_bytes + bound_bytes);
   if (rc) return rc;
-  int4 *vbox = (int4 *)ctx->scratch.ptr;
-  const float half_w = (float)(0.5 * W), half_h = (float)(0.5 * H);
-  vertex_box_init_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, stream>>>(vbox, n_pairs);
-  ctx->launches += 1;
-  if (T > 0 && total > 0) {
-    vertex_box_kernel<<<dim3((T + 255) / 256, B), 256, 0, stream>>>(verts, tris, V, T, W, H, half_w, half_h, vbox);
-    ctx->launches += 1;
+  char *base = (char *)ctx->scratch.ptr;
+  uint2 *buffers[2] = {(uint2 *)base, (uint2 *)(base + entry_bytes)};
+  unsigned *counts = (unsigned *)(base + 2 * entry_bytes);
+  uint2 *bounds = (uint2 *)(base + 2 * entry_bytes + count_bytes);
+  EntrySource src;
+  src.sorted = nullptr; src.ids = ids; src.tris = tris; src.bary = bary; src.V = V;
+  const dim3 sort_grid((tiles + kSortWarps - 1) / kSortWarps, B);
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = pass * digit_bits;
+    const unsigned mask = (1u << digit_bits) - 1u;
+    uint2 *out = buffers[pass & 1];
+    sort_count_kernel<<<sort_grid, kSortWarps * 32, 0, stream>>>(src, entries, (size_t)ppi, tiles, shift, mask, counts);
+    sort_scan_kernel<<<B, 1024, 0, stream>>>(counts, kSortBins * tiles);
+    sort_scatter_kernel<<<sort_grid, kSortWarps * 32, 0, stream>>>(src, entries, (size_t)ppi, tiles, shift, mask, counts, out);
+    ctx->launches += 3;
+    src.sorted = out;
   }
+  const uint2 *sorted = src.sorted;
+  PMR_CUDA(ctx, cudaMemsetAsync(bounds, 0, bound_bytes, stream));
+  segment_bounds_kernel<<<dim3((entries + 255) / 256, B), 256, 0, stream>>>(sorted, entries, V, bounds);
+  ctx->launches += 1;
   const int ncomp = 3 + (fused ? A : 0);
-  const size_t smem = (size_t)kOrderedWarps * 32 * 3 * ncomp * sizeof(float);
-  const unsigned grid = (unsigned)((n_pairs + kOrderedWarps - 1) / kOrderedWarps);
-  if (fused) {
-    PMR_CUDA(ctx, cudaFuncSetAttribute(backward_ordered_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    backward_ordered_kernel<true><<<grid, kOrderedWarps * 32, smem, stream>>>(grad, verts, attrs, tris, ids, bary,
-                                                                            vbox, V, A, W, H, n_pairs, d_verts, d_attrs);
-  } else {
-    backward_ordered_kernel<false><<<grid, kOrderedWarps * 32, smem, stream>>>(grad, verts, attrs, tris, ids, bary,
-                                                                             vbox, V, A, W, H, n_pairs, d_verts, d_attrs);
+  const size_t smem = (size_t)kFoldWarps * (32 * ncomp + 32) * sizeof(float);
+  // vertices per warp: enough to keep the 32 lanes busy (about 512 entries per warp when the runs are short)
+  long long per_vertex = 3 * ppi / (V > 0 ? V : 1);
+  int vpw = (int)(512 / (per_vertex > 0 ? per_vertex : 1));
+  vpw = vpw < 1 ? 1 : (vpw > 32 ? 32 : vpw);
+  const int groups = (V + vpw - 1) / vpw;
+  const dim3 fold_grid((groups + kFoldWarps - 1) / kFoldWarps, B);
+#define PMR_FOLD(F, AS)                                                                                       \
+  {                                                                                                           \
+    PMR_CUDA(ctx, cudaFuncSetAttribute(backward_fold_kernel<F, AS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    backward_fold_kernel<F, AS><<<fold_grid, kFoldWarps * 32, smem, stream>>>(                                \
+        grad, verts, attrs, tris, ids, bary, sorted, bounds, entries, V, A, (size_t)ppi, vpw, groups, d_verts, d_attrs); \
   }
+  if (!fused) PMR_FOLD(false, 0)
+  else if (A == 9) PMR_FOLD(true, 9)
+  else if (A == 4) PMR_FOLD(true, 4)
+  else PMR_FOLD(true, 0)
+#undef PMR_FOLD
   ctx->launches += 1;
-  return check_launch(ctx, "backward_ordered_kernel");
+  return check_launch(ctx, "backward_fold_kernel");
 }
 
 }  // namespace pmr

@@ -42,9 +42,9 @@ def test_reference_autograd_function_on_the_dropin(reference_on_b200, name):
     t = torch.from_numpy(g["triangles"]).cuda()
     ids, bary, z = ext.BarycentricRasterizer.apply(v, t, W, H)
     assert ids.is_cuda and bary.is_cuda and z.is_cuda
-    assert_bits(ids.cpu().numpy(), g["ids"], name + " ids")
+    assert_bits(ids.detach().cpu().numpy(), g["ids"], name + " ids")
     assert_bits(bary.detach().cpu().numpy(), g["bary"], name + " bary")
-    assert_bits(z.cpu().numpy(), g["z"], name + " z")
+    assert_bits(z.detach().cpu().numpy(), g["z"], name + " z")
     bary.backward(torch.from_numpy(g["df_dbary"]).cuda())
     assert_bits(v.grad.cpu().numpy(), g["df_dvertices"], name + " df_dvertices (reference order)")
 
@@ -52,9 +52,10 @@ def test_reference_autograd_function_on_the_dropin(reference_on_b200, name):
 @pytest.mark.parametrize("name", _cases("clip_vertices", "attributes", "out", "grad_out", "d_clip_vertices", "d_attributes"))
 def test_reference_rasterize_clip_space_on_the_dropin(reference_on_b200, name):
     """The reference's rasterize_clip_space (rast.py:66-152: its Python loop over images, index_select, gather,
-    mul, sum, clamp, blend) fed CUDA tensors, the kernel calls landing in libpmr_b200.so: image and d(vertices)
-    bit-equal to the reference's own run on its CPU kernel (the goldens); d(attributes) comes from torch's
-    index_put_ on the GPU here (atomics), so it is compared with the tolerance of the north star."""
+    mul, sum, clamp, blend) fed CUDA tensors, the kernel calls landing in libpmr_b200.so: image within the
+    north-star tolerance of the reference's own run on its CPU kernel (the goldens; torch's CUDA ops around the
+    kernel need not round like its CPU ops), gradients within 2e-5 of the largest entry (d(attributes) comes from
+    torch's index_put_ on the GPU here: atomics)."""
     from conftest import assert_close
     rast, _ = reference_on_b200
     g = load_golden(name)
@@ -65,7 +66,9 @@ def test_reference_rasterize_clip_space_on_the_dropin(reference_on_b200, name):
     out = rast.rasterize_clip_space(cv, at, dev(g["triangles"]), W, H, dev(g["background"]))
     assert out.is_cuda
     out.backward(dev(g["grad_out"]))
-    assert_bits(out.detach().cpu().numpy(), g["out"], name + ": image through the reference's torch ops")
+    # torch's CUDA mul / sum kernels need not round like its CPU kernels (one attribute: a different order of
+    # the three corner products); ids and barycentrics underneath are bit-exact (test above)
+    assert_close(out.detach().cpu().numpy(), g["out"], name + ": image through the reference's torch ops")
     # d(bary) is reduced over the attribute axis by torch's CUDA sum here and by its CPU sum in the golden run:
     # same terms, different order
     scale = np.abs(g["d_clip_vertices"]).max() + 1e-30
