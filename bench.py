@@ -323,7 +323,7 @@ KERNEL_NAMES = {"scatter": "scatter_small_kernel (small triangles -> packed dept
 
 
 def measure_on_device(sc, device, mode, steps, warmup, rank=0, world=1, collective="peer", sample_clocks=True,
-                      grad_seed=1):
+                      grad_seed=1, use_graph=True):
     """Device-timed steps of one workload on this rank's slice of it.  Returns a dict with ms_per_step (max
     over ranks), per-stage times from the library's own CUDA-event pairs, launch count, clocks and sizes."""
     import numpy as np
@@ -398,28 +398,68 @@ def measure_on_device(sc, device, mode, steps, warmup, rank=0, world=1, collecti
                               "max_abs_value": scale, "finite": bool(torch.isfinite(via_peers).all().item())}
             if not exchange_check["all_ranks_bit_identical"] or not exchange_check["finite"] or err > 1e-3 * scale:
                 raise RuntimeError("peer exchange check failed: %s" % (exchange_check,))
+        # Per-stage times and the launch count come from a short eager pass (the library's own CUDA-event pairs);
+        # the timed steps then replay ONE CUDA graph of the whole step -- the same kernels, without the host's
+        # launch gaps between them (about a dozen launches of 0.02 - 0.6 ms each per step).  All ranks take the
+        # same decision.
+        _lib.enable_stage_timing(local, True)
+        _lib.read_stage_timing(local, reset=True)
+        launches0 = _lib.launch_count(local)
+        stage_steps = max(3, min(steps, 10))
+        for _ in range(stage_steps):
+            step()
+        torch.cuda.synchronize()
+        launches_per_step = (_lib.launch_count(local) - launches0) / stage_steps
+        stages = _lib.read_stage_timing(local, reset=True)
+        _lib.enable_stage_timing(local, False)
+        graph, graph_note = None, "eager launches"
+        if use_graph:
+            try:
+                side = torch.cuda.Stream(device)
+                side.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        step()
+                torch.cuda.current_stream(device).wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    captured = step()
+                graph.replay()
+                torch.cuda.synchronize()
+                if not bool(torch.isfinite(captured).all().item()):
+                    raise RuntimeError("graph replay produced non-finite gradients")
+                graph_note = "one CUDA graph of the step, replayed"
+            except Exception as e:                       # noqa: BLE001 -- fall back to eager launches, say so
+                graph, graph_note = None, "eager launches (graph capture failed: %s: %s)" % (type(e).__name__, str(e)[:200])
+                torch.cuda.synchronize()
+        if world > 1:                                    # everybody or nobody
+            ok = torch.tensor([1 if (graph is not None or not use_graph) else 0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if use_graph and int(ok.item()) == 0:
+                graph, graph_note = None, "eager launches (a rank could not capture the step)"
+        run = graph.replay if graph is not None else step
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
         sampler = ClockSampler(local if (rank == 0 and sample_clocks) else None)   # one sampler per job
         sampler.start()                                              # returns once samples are flowing
         if world > 1:
             dist.barrier()
         sampler.t_begin = time.time()
-        _lib.enable_stage_timing(local, True)
-        _lib.read_stage_timing(local, reset=True)
-        launches0 = _lib.launch_count(local)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(steps):
-            step()
+            run()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         ms_total = e0.elapsed_time(e1)
-        launches = _lib.launch_count(local) - launches0
-        stages = _lib.read_stage_timing(local, reset=True)
-        _lib.enable_stage_timing(local, False)
+        launches = int(round(launches_per_step * steps))
         clocks = sampler.stop()
+        del graph
     if world > 1:
         t = torch.tensor([ms_total], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -431,7 +471,8 @@ def measure_on_device(sc, device, mode, steps, warmup, rank=0, world=1, collecti
     if timed_out:
         raise RuntimeError("peer exchange: a rank stopped waiting for a peer's partial sums; the result is invalid")
     del grad
-    return {"ms_per_step": ms_total / steps, "stages": stages, "steps": steps, "launches": int(launches),
+    return {"ms_per_step": ms_total / steps, "stages": stages, "steps": steps, "stage_steps": stage_steps,
+            "launches": int(launches), "launch_mode": graph_note,
             "clocks": clocks, "B": B, "V": V, "T": T, "H": H, "W": W, "shared_mesh": shared_mesh,
             "exchange_check": exchange_check,
             "exchange": "peer" if (shared_mesh and world > 1 and collective == "peer" and not timed_out and exchange is not None)
@@ -445,7 +486,7 @@ def roofline_of(m, mode, total_pixels_job=None):
     B, V, T, H, W = m["B"], m["V"], m["T"], m["H"], m["W"]
     P = B * H * W
     bytes_fwd, bytes_bwd, kernel_bytes = algorithmic_bytes(P, B, V, T)
-    stages, steps, ms_step = m["stages"], m["steps"], m["ms_per_step"]
+    stages, steps, ms_step = m["stages"], m["stage_steps"], m["ms_per_step"]
     stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
     per_step = {k: v[0] / steps for k, v in stages.items()}
     dominant = max(kernel_bytes, key=lambda k: per_step[k])
@@ -624,6 +665,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the c1 / c3 / c4 / c5 lines of the default N = 1 run")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step from the host instead of replaying a CUDA graph")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="shared-mesh gradient over the ranks: fused push + reduce over peer memory, or kernel + NCCL all-reduce")
     args = ap.parse_args()
@@ -675,10 +717,11 @@ def main():
         full = make_workload("c4")
         if rank == 0:
             # the same job on one GPU, timed inside this run: the one-GPU reference of the strong-scaling line
-            m1 = measure_on_device(full, device, args.mode, max(3, min(args.steps, 10)), 3, sample_clocks=False)
+            m1 = measure_on_device(full, device, args.mode, max(3, min(args.steps, 10)), 3, sample_clocks=False,
+                                   use_graph=not args.no_graph)
             single_gpu = {"ms_per_step": m1["ms_per_step"], "views": m1["B"],
                           "value": m1["B"] * m1["H"] * m1["W"] / (m1["ms_per_step"] * 1e-3) / 1e6, "unit": UNIT,
-                          "stages_ms_per_step": {k: v[0] / m1["steps"] for k, v in m1["stages"].items()}}
+                          "stages_ms_per_step": {k: v[0] / m1["stage_steps"] for k, v in m1["stages"].items()}}
             del m1
             torch.cuda.empty_cache()
         mine = D.shard_views(full["clip_vertices"].shape[0], rank, world)
@@ -696,7 +739,8 @@ def main():
             sc["camera_matrices"] = S.orbit_cameras(B_local * world)[mine.start:mine.stop]
             sc["clip_vertices"] = S.transform(sc["camera_matrices"], sc["world_vertices"])
 
-    m = measure_on_device(sc, device, args.mode, args.steps, args.warmup, rank, world, args.collective)
+    m = measure_on_device(sc, device, args.mode, args.steps, args.warmup, rank, world, args.collective,
+                          use_graph=not args.no_graph)
     B, V, T, H, W = m["B"], m["V"], m["T"], m["H"], m["W"]
     P = B * H * W
     ms_step = m["ms_per_step"]
@@ -739,7 +783,8 @@ def main():
         for name in ("c1", "c3", "c4", "c5"):
             try:
                 sc_k = make_workload(name)
-                m_k = measure_on_device(sc_k, device, args.mode, 10 if name != "c5" else 5, 3, sample_clocks=False)
+                m_k = measure_on_device(sc_k, device, args.mode, 10 if name != "c5" else 5, 3, sample_clocks=False,
+                                        use_graph=not args.no_graph)
                 r_k = roofline_of(m_k, args.mode)
                 n_img = m_k["B"]
                 fp32_roofline(sc_k, m_k, r_k, m["clocks"], images=tuple(range(0, n_img, max(1, n_img // 4)))[:4])
@@ -749,6 +794,7 @@ def main():
                 configs.append({
                     "workload": WORKLOADS[name], "batch": m_k["B"], "triangles": m_k["T"], "vertices": m_k["V"],
                     "image": [m_k["H"], m_k["W"]], "steps": m_k["steps"], "ms_per_step": m_k["ms_per_step"],
+                    "launches": m_k["launch_mode"],
                     "value": P_k / (m_k["ms_per_step"] * 1e-3) / 1e6, "unit": UNIT,
                     "stages_ms_per_step": r_k["stages_ms_per_step"],
                     "hbm_frac_step": r_k["step"]["frac"], "hbm_frac_forward": r_k["forward"]["frac"],
@@ -778,6 +824,7 @@ def main():
                        "triangles_per_s": job_pixels / (H * W) * T / (ms_step * 1e-3),
                        "l2": "per-step working set %.2f GB exceeds the 126 MB L2; no explicit flush" % (bytes_total / 1e9),
                        "vertex_stage": "world->clip kernel + view-summed backward inside the step" if m["shared_mesh"] else "none",
+                       "launches": m["launch_mode"] + "; per-stage times from %d eager steps before the timed ones" % m["stage_steps"],
                        "collective": exchange_text},
             "roofline": roofline, "parity": parity, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": m["launches"], "clocks": m["clocks"],

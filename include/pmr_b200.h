@@ -185,8 +185,11 @@ PMR_API int pmr_transform_backward(pmr_context *ctx, const float *matrices, cons
  * opens every peer's handle with pmr_peer_open, and the ranks meet at a host barrier before the first step.
  * peer_buffers[r] is rank r's buffer as mapped in THIS process (own allocation at [rank]).  `epoch` counts the
  * calls on this set of buffers from 1 (below 2^30: PMR_ERR_SIZE after that, allocate a new set) and must be the
- * same number on every rank for the same step.  A rank whose
- * peer does not deliver within ~2 s gives up waiting (pmr_peer_status reports 1) instead of hanging the device.
+ * same number on every rank for the same step; 0 lets the device count (a step counter in the rank's own
+ * buffer): the call then has no per-step argument and can be captured in a CUDA graph and replayed.  Use one
+ * convention per set of buffers.  A rank whose peer does not deliver within PMR_PEER_WAIT_SECONDS (default 10 s)
+ * gives up waiting instead of hanging the device: pmr_peer_status reports 1 from then on and this and every
+ * later call on the buffers fills d_world_vertices with NaN -- check the status before using the gradient.
  * Teardown: host barrier, pmr_peer_close on the opened pointers, pmr_peer_free on the own one.  world <= PMR_MAX_PEERS.
  */
 #define PMR_MAX_PEERS 16

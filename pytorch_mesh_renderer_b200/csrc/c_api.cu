@@ -461,7 +461,7 @@ int pmr_transform_backward_exchange(pmr_context *ctx, const float *matrices, con
   if (B < 0 || V < 0) return set_error(ctx, PMR_ERR_INVALID, "negative batch/vertex count");
   if (world < 1 || world > PMR_MAX_PEERS || rank < 0 || rank >= world)
     return set_error(ctx, PMR_ERR_INVALID, "rank / world outside 0 <= rank < world <= PMR_MAX_PEERS");
-  if (epoch < 1) return set_error(ctx, PMR_ERR_INVALID, "epochs count from 1");
+  if (epoch < 0) return set_error(ctx, PMR_ERR_INVALID, "epochs count from 1 (0: counted on the device)");
   if (epoch >= (1ll << 30))   // the flags carry the epoch as a 30-bit stamp compared with <
     return set_error(ctx, PMR_ERR_SIZE, "2^30 exchange steps on one set of buffers: allocate a new set");
   if (!matrices || !d_clip_vertices || !d_world_vertices || !peer_buffers)

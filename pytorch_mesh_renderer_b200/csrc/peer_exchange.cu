@@ -11,7 +11,9 @@
 // all-reduce -- every rank adds the same numbers in the same order, so all ranks hold bit-identical sums.
 //
 // Exchange buffer of a rank (pmr_peer_alloc, zero-initialised):
-//   line 0                  CTA ticket counter of the push kernel
+//   line 0                  CTA ticket counter of the push kernel and, 64 bytes in, the step counter (the epoch of the
+//                           last push launched here: `epoch` = 0 in the call means "the next one", which keeps
+//                           the pair of kernels free of per-step arguments -- capturable in a CUDA graph)
 //   line 1                  status word (1 = a wait timed out; sticky) and, 64 bytes in, the local "go" word
 //                           (epoch whose partials have all arrived; written by CTA 0 of the reduction)
 //   lines 2 ..              flags[parity][peer], one 128-byte line each: last epoch peer `peer` has delivered
@@ -31,6 +33,7 @@ constexpr int kLine = 128;                               // bytes per flag line
 constexpr int kHeaderLines = 2 + 2 * PMR_MAX_PEERS;
 constexpr size_t kHeaderBytes = (size_t)kHeaderLines * kLine;
 constexpr int kGoOffset = kLine + 64;                    // byte offset of the "go" word
+constexpr int kStepOffset = 64;                          // byte offset of the step counter
 
 struct PeerTable {
   char *base[PMR_MAX_PEERS];
@@ -58,9 +61,14 @@ __device__ __forceinline__ int load_acquire_system(const int *p) {
 // slot [parity][rank] of every peer; the last CTA to finish raises flag [parity][rank] = epoch on every peer.
 __global__ void __launch_bounds__(256)
 transform_backward_push_kernel(const float *__restrict__ matrices, const float4 *__restrict__ d_clip, int B, int V,
-                               PeerTable peers, int rank, int world, int parity, int epoch, long long n_pad) {
+                               PeerTable peers, int rank, int world, int epoch_arg, long long n_pad) {
   extern __shared__ float ms[];                          // [B][12]: columns 0..2 of every row of M_b
   __shared__ bool last_cta;
+  // the step: given, or the successor of the last one pushed from this buffer (written back by the last CTA, so
+  // every CTA of this launch reads the same value)
+  int *step_counter = reinterpret_cast<int *>(peers.base[rank] + kStepOffset);
+  const int epoch = epoch_arg > 0 ? epoch_arg : ((*reinterpret_cast<volatile int *>(step_counter) + 1) & 0x3fffffff);
+  const int parity = epoch & 1;
   for (int i = threadIdx.x; i < B * 12; i += blockDim.x) {
     const int bb = i / 12, r = (i % 12) / 3, k = i % 3;
     ms[i] = matrices[(size_t)bb * 16 + r * 4 + k];
@@ -91,6 +99,7 @@ transform_backward_push_kernel(const float *__restrict__ matrices, const float4 
     if (last_cta) {
       __threadfence_system();                            // acquire side of the ticket: the other CTAs' stores
       *counter = 0;                                      // next launch on this stream starts from zero
+      *step_counter = epoch;                             // every CTA has read the old value by now (it drew a ticket)
     }
   }
   __syncthreads();
@@ -104,9 +113,12 @@ transform_backward_push_kernel(const float *__restrict__ matrices, const float4 
 // publishes the epoch in the local "go" word, which the other CTAs of the grid wait for (device scope) -- CTA 0
 // is in the first wave of every launch, so they never wait for a CTA that cannot run.
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(char *base, int world, int parity, int epoch, long long n, long long n_pad,
+reduce_partials_kernel(char *base, int world, int epoch_arg, long long n, long long n_pad,
                        long long wait_cycles, float *__restrict__ out) {
   __shared__ int failed;
+  // the step of the push kernel launched just before this one on the same stream
+  const int epoch = epoch_arg > 0 ? epoch_arg : *reinterpret_cast<volatile int *>(base + kStepOffset);
+  const int parity = epoch & 1;
   int *status = reinterpret_cast<int *>(base + kLine);
   int *go = reinterpret_cast<int *>(base + kGoOffset);
   if (threadIdx.x == 0) failed = 0;
@@ -175,13 +187,13 @@ int transform_backward_exchange_impl(Context *ctx, const float *matrices, const 
   PeerTable table;
   for (int r = 0; r < PMR_MAX_PEERS; ++r) table.base[r] = r < world ? static_cast<char *>(peers[r]) : nullptr;
   const long long n = (long long)V * 3, n_pad = padded(n);
-  const int parity = (int)(epoch & 1), stamp = (int)(epoch & 0x3fffffff);
+  const int stamp = (int)(epoch & 0x3fffffff);             // 0: the kernels take the step from the buffer
   const size_t smem = (size_t)B * 12 * sizeof(float);
   if (smem > 48 * 1024) return set_error(ctx, PMR_ERR_SIZE, "too many views for one transform_backward launch");
   transform_backward_push_kernel<<<(V + 255) / 256, 256, smem, stream>>>(
-      matrices, reinterpret_cast<const float4 *>(d_clip), B, V, table, rank, world, parity, stamp, n_pad);
+      matrices, reinterpret_cast<const float4 *>(d_clip), B, V, table, rank, world, stamp, n_pad);
   reduce_partials_kernel<<<(unsigned)((n_pad / 4 + 255) / 256), 256, 0, stream>>>(
-      table.base[rank], world, parity, stamp, n, n_pad, ctx->peer_wait_cycles, d_world);
+      table.base[rank], world, stamp, n, n_pad, ctx->peer_wait_cycles, d_world);
   ctx->launches += 2;
   return check_launch(ctx, "transform_backward_push_kernel / reduce_partials_kernel");
 }

@@ -911,7 +911,9 @@ backward_fold_kernel(const float *__restrict__ grad, const float *__restrict__ v
 static int strip_blocks_for(const Context *ctx, int W, int H, int B) {
   if (ctx->strip_blocks_override > 0) return ctx->strip_blocks_override;
   const long long block_rows = (long long)((H + 3) / 4) * B;
-  const long long wanted = 4LL * 32 * ctx->sm_count;
+  // a dozen waves of 8 CTAs x 4 warps per SM: with fewer, the last, partly filled wave shows (c4 at 32 views
+  // per GPU ran 6.9 waves with strips of 8)
+  const long long wanted = 12LL * 32 * ctx->sm_count;
   for (int n = 8; n > 1; n >>= 1)
     if (block_rows * ((W + 8 * n - 1) / (8 * n)) >= wanted) return n;
   return 1;

@@ -139,17 +139,20 @@ class SharedGradientExchange:
         B, V, _ = d_clip.shape
         if V != self.vertex_count:
             raise ValueError("exchange was created for %d vertices, got %d" % (self.vertex_count, V))
-        self.epoch += 1                    # one set of buffers serves 2^30 steps (the library refuses more)
+        self.epoch += 1                    # bookkeeping only: the device counts the steps itself (epoch argument 0),
+        #                                    so that the call has no per-step argument and replays from a CUDA graph
         out = torch.empty((V, 3), dtype=torch.float32, device=d_clip.device)
         with torch.cuda.device(d_clip.device):
             rc = _lib.load().pmr_transform_backward_exchange(
-                self.ctx, _lib.ptr(matrices), _lib.ptr(d_clip), B, V, self.peers, self.rank, self.world, self.epoch,
+                self.ctx, _lib.ptr(matrices), _lib.ptr(d_clip), B, V, self.peers, self.rank, self.world, 0,
                 _lib.ptr(out), _lib.stream_ptr(d_clip.device))
         _lib.check(self.ctx, rc)
         return out
 
     def timed_out(self):
-        """True if a wait for a peer ever gave up (synchronises the device)."""
+        """True if a wait for a peer ever gave up (synchronises the device).  From that moment every reduce() on
+        these buffers returns NaN instead of a sum of stale partials; check before the optimizer step when a rank
+        may stall for longer than PMR_PEER_WAIT_SECONDS (default 10 s)."""
         status = ctypes.c_int(0)
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
@@ -160,8 +163,12 @@ class SharedGradientExchange:
         if self.own is None and not self.opened:
             return
         lib = _lib.load()
+        failed = False
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
+            if self.own is not None:
+                status = ctypes.c_int(0)
+                failed = lib.pmr_peer_status(self.ctx, self.own, ctypes.byref(status)) == 0 and status.value != 0
             if collective:
                 dist.barrier(group=self.group)     # nobody stores into a buffer that is about to go away
             for p in self.opened:
@@ -169,6 +176,9 @@ class SharedGradientExchange:
             if self.own is not None:
                 lib.pmr_peer_free(self.ctx, self.own)
         self.opened, self.own = [], None
+        if failed:
+            raise _lib.PmrError("peer exchange: a wait for a peer's partial sums gave up during this run; the "
+                                "gradients returned from that step on were NaN")
 
 
 def rasterize_shared_mesh(world_vertices, attributes, triangles, camera_matrices, image_width, image_height,

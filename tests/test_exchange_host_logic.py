@@ -128,13 +128,14 @@ def test_successful_setup_fills_the_peer_table_and_counts_epochs(fake_world, mon
         table = [ex.peers[r] for r in range(3)]
         assert table[rank] == 0x1000 * (rank + 1)                                  # own allocation at [rank]
         assert all(table[r] == 0x1000 * (r + 1) + 0x100000 * (rank + 1) for r in range(3) if r != rank)
-    # steps: the library sees epochs 1, 2, ... and the same table
+    # steps: the library is told to count the steps on the device (epoch argument 0: nothing in the call changes
+    # from step to step, so it replays from a CUDA graph) and sees the same table; the wrapper keeps its own count
     rank, ex = 1, results[1]
     monkeypatch.setattr(_lib, "load", lambda: libs[rank])
     for _ in range(3):
         out = ex.reduce(torch.zeros(2, 4, 4), torch.zeros(2, 5, 4))
         assert out.shape == (5, 3)
-    assert libs[rank].epochs == [1, 2, 3]
+    assert libs[rank].epochs == [0, 0, 0] and ex.epoch == 3
     assert libs[rank].peers_seen == [ex.peers[r] for r in range(3)]
     with pytest.raises(ValueError, match="created for 5 vertices"):
         ex.reduce(torch.zeros(2, 4, 4), torch.zeros(2, 6, 4))
