@@ -2,18 +2,18 @@
 // optionally fused with the backward of the attribute interpolation (autograd of
 // rast.py:118-150), in two accumulation modes:
 //
-//   PMR_BACKWARD_ATOMIC   backward_blocks_kernel: one warp per 8x4 pixel block; the per-pixel sums are
-//                         parked in shared memory, rows sorted by triangle, and lane c adds column c
-//                         over each triangle's rows: one fire-and-forget atomic per (block, triangle,
-//                         column).  fp32 sums in arbitrary order.  (Attribute counts without a
-//                         specialised instance fall back to backward_atomic_kernel, one thread per
-//                         pixel.)  With SHADE it is also the backward of the fused render path.
-//   PMR_BACKWARD_ORDERED  one warp per (image, vertex): walks the union of the pixel boxes of the
-//                         vertex's triangles in ascending pixel order, lanes evaluate the
-//                         per-pixel terms in parallel and the sums are then folded strictly in
-//                         pixel order, corner 0..2 within a pixel -- the reference's summation
-//                         order (K.cpp:156-157, :232-269; index_put_ order of rast.py:130-132),
-//                         so the result is bit-reproducible and equals the reference's.
+//   PMR_BACKWARD_ATOMIC   backward_blocks_kernel: one warp per strip of 8x4 pixel blocks, the per-pixel inputs
+//                         fetched by TMA; the per-pixel sums are parked in shared memory as rows of float4
+//                         slots, rows sorted by triangle, and a lane adds four columns over a triangle's rows:
+//                         one fire-and-forget atomic per (block, triangle, column).  fp32 sums in arbitrary
+//                         order over the reference's per-pixel terms.  (Attribute counts without a specialised
+//                         instance fall back to backward_atomic_kernel, one thread per pixel.)  With SHADE it is
+//                         also the backward of the fused render path.
+//   PMR_BACKWARD_ORDERED  a stable radix sort of the (pixel, corner) entries by vertex id, then one warp per
+//                         run of vertices folds the entries' terms strictly in entry order -- pixel ascending,
+//                         corner 0..2 within a pixel: the reference's summation order (K.cpp:156-157, :232-269;
+//                         index_put_ order of rast.py:130-132), so the result is bit-reproducible and equals the
+//                         reference's.
 //
 // Per-pixel arithmetic is shared with the forward pass (raster_math.cuh) and follows the
 // reference op for op; compile with -fmad=false.
@@ -997,8 +997,12 @@ int backward_impl(Context *ctx, const float *df_dbary, const float *grad_image, 
   StageScope timed(ctx, PMR_STAGE_BACKWARD, stream);
 
   if (mode == PMR_BACKWARD_ATOMIC) {
-    if (d_verts) PMR_CUDA(ctx, cudaMemsetAsync(d_verts, 0, (size_t)n_pairs * 4 * sizeof(float), stream));
-    if (fused && d_attrs) PMR_CUDA(ctx, cudaMemsetAsync(d_attrs, 0, (size_t)n_pairs * A * sizeof(float), stream));
+    if (d_verts && fused && d_attrs == d_verts + (size_t)n_pairs * 4) {      // one allocation: one memset
+      PMR_CUDA(ctx, cudaMemsetAsync(d_verts, 0, (size_t)n_pairs * (4 + A) * sizeof(float), stream));
+    } else {
+      if (d_verts) PMR_CUDA(ctx, cudaMemsetAsync(d_verts, 0, (size_t)n_pairs * 4 * sizeof(float), stream));
+      if (fused && d_attrs) PMR_CUDA(ctx, cudaMemsetAsync(d_attrs, 0, (size_t)n_pairs * A * sizeof(float), stream));
+    }
     if (total == 0 || T == 0) return PMR_OK;
     const int strip = strip_blocks_for(ctx, W, H, B);
     BlockMaps maps;

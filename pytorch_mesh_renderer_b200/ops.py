@@ -174,8 +174,13 @@ def rasterize_interpolate_backward(grad_image, vertices, attributes, triangles, 
         raise ValueError("grad_output must have shape %s, got %s" % (tuple(i.shape) + (A,), tuple(g.shape)))
     H, W = i.shape[1], i.shape[2]
     dev = v.device
-    dv = torch.empty((B, V, 4), dtype=torch.float32, device=dev) if need_vertices else None
-    da = torch.empty((B, V, A), dtype=torch.float32, device=dev) if need_attributes else None
+    if need_vertices and need_attributes:
+        # one allocation: the library then clears both gradients with one memset
+        both = torch.empty((B * V * (4 + A),), dtype=torch.float32, device=dev)
+        dv, da = both[:B * V * 4].view(B, V, 4), both[B * V * 4:].view(B, V, A)
+    else:
+        dv = torch.empty((B, V, 4), dtype=torch.float32, device=dev) if need_vertices else None
+        da = torch.empty((B, V, A), dtype=torch.float32, device=dev) if need_attributes else None
     ctx = _lib.context(dev.index)
     with torch.cuda.device(dev):
         rc = _lib.load().pmr_rasterize_interpolate_backward(
