@@ -270,7 +270,7 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
   constexpr int E = R::E, U = R::U, J = R::J, ROW4 = R::ROW4, SLOTS = R::SLOTS;
   constexpr int GC = SHADE ? 4 : (FUSED ? A : 3);    // gradient channels per pixel
   // the reduction reads up to kPieceRows - 1 rows past a piece (values unused): they must stay inside the area
-  constexpr int kTail = 32 * 16 + 32 * 4 + 96 * 4 + 32 * GC * 4 + 8 + 64;
+  constexpr int kTail = 32 * 16 + 32 * 4 + 96 * 4 + 32 * GC * 4 + 8 + 64 + 32;
   constexpr int kNeeded = (kPieceRows - 1) * ROW4 * 16;
   struct __align__(128) WarpArea {
     float4 rows[32 * ROW4];                  // 32 rows of ROW4 float4 slots
@@ -280,6 +280,7 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
     float grad[32 * GC];
     unsigned long long ready;                // their mbarrier (one fetch is in flight at a time)
     unsigned short pieces[32];               // per piece: first row | rows << 8 | continues the previous piece's group << 15
+    unsigned char order[32];                 // row -> the pixel (lane of the block's raster order) that owns it
     char pad[kNeeded > kTail ? kNeeded - kTail : 1];
   };
   static_assert(offsetof(WarpArea, ids) % 128 == 0 && offsetof(WarpArea, bary) % 128 == 0 &&
@@ -340,9 +341,8 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
   }
 
   for (int it = 0; it < n_blocks; ++it) {
-    int id = -1;
-    float bp[3] = {0.0f, 0.0f, 0.0f};
-    float g_local[SHADE ? 9 : GC];
+    // ---- the block's pixels in raster order: triangle id, coverage
+    int id0 = -1;
     {
       const Where w = where();
       const int lane = w.lane, iy = w.y0 + (lane >> 3), ix = xs + it * 8 + (lane & 7);
@@ -357,21 +357,69 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
         }
         const WarpArea &area = *w.area;
         if (in_image) {
-          id = area.ids[lane];
-          bp[0] = area.bary[3 * lane]; bp[1] = area.bary[3 * lane + 1]; bp[2] = area.bary[3 * lane + 2];
+          id0 = area.ids[lane];
+          if (id0 == 0) {           // K.cpp:162: id 0 with barycentrics summing below 0.9 draws nothing
+            const float b3[3] = {area.bary[3 * lane], area.bary[3 * lane + 1], area.bary[3 * lane + 2]};
+            if (!pixel_is_covered(0, b3)) id0 = -1;
+          }
         }
+      } else if (in_image) {
+        const size_t px = ((size_t)b * H + iy) * W + ix;
+        id0 = ids[px];
+        if (id0 == 0) {
+          const float b3[3] = {bary[3 * px], bary[3 * px + 1], bary[3 * px + 2]};
+          if (!pixel_is_covered(0, b3)) id0 = -1;
+        }
+      }
+    }
+    const unsigned covered_lanes = __ballot_sync(0xffffffffu, id0 >= 0);
+    if (covered_lanes == 0u) {
+      if (use_tma && it + 1 < n_blocks) {
+        __syncwarp();
+        fetch_block(where(), it + 1);
+      }
+      continue;
+    }
+
+    // ---- sort the block's pixels by triangle: lane L takes over the pixel whose ROW is L.  The rows of one
+    // triangle are consecutive (groups ordered by their first lane, uncovered pixels last), and because a
+    // lane later writes row `lane`, the 128-bit row stores of a quarter warp go to eight consecutive rows --
+    // conflict-free, where rows in raster order of the pixels cost 7.6 wavefronts per store instead of 4.
+    int id, rank, group_size;
+    float bp[3] = {0.0f, 0.0f, 0.0f};
+    float g_local[SHADE ? 9 : GC];
+    {
+      const Where w = where();
+      const int lane = w.lane;
+      WarpArea &area = *w.area;
+      const unsigned peers0 = __match_any_sync(0xffffffffu, id0 >= 0 ? id0 : -1 - lane);
+      const int leader0 = __ffs(peers0) - 1;
+      const int size0 = __popc(peers0), rank0 = __popc(peers0 & ((1u << lane) - 1u));
+      const int lead_size = (id0 >= 0 && lane == leader0) ? size0 : 0;
+      const int before = warp_inclusive_scan(lead_size) - lead_size;      // rows of the groups led by lower lanes
+      const int group_row = __shfl_sync(0xffffffffu, before, leader0);    // by all lanes: not under the condition
+      const int row0 = id0 >= 0 ? group_row + rank0
+                                : __popc(covered_lanes) + __popc(~covered_lanes & ((1u << lane) - 1u));
+      area.order[row0] = (unsigned char)lane;
+      __syncwarp();
+      const int src = area.order[lane];          // the pixel (lane of the raster order) this lane takes over
+      id = __shfl_sync(0xffffffffu, id0, src);
+      rank = __shfl_sync(0xffffffffu, rank0, src);
+      group_size = __shfl_sync(0xffffffffu, size0, src);
+      if (use_tma) {
+        bp[0] = area.bary[3 * src]; bp[1] = area.bary[3 * src + 1]; bp[2] = area.bary[3 * src + 2];
         if constexpr (SHADE) {
-          const float4 g4 = reinterpret_cast<const float4 *>(area.grad)[(3 - (lane >> 3)) * 8 + (lane & 7)];
+          const float4 g4 = reinterpret_cast<const float4 *>(area.grad)[(3 - (src >> 3)) * 8 + (src & 7)];
           g_local[0] = g4.x; g_local[1] = g4.y; g_local[2] = g4.z;
         } else {
 #pragma unroll
-          for (int a = 0; a < GC; ++a) g_local[a] = area.grad[lane * GC + a];
+          for (int a = 0; a < GC; ++a) g_local[a] = area.grad[src * GC + a];
         }
         __syncwarp();                             // the boxes are consumed by every lane before they are refilled
         if (it + 1 < n_blocks) fetch_block(w, it + 1);              // lands while this block is processed
-      } else if (in_image) {
+      } else if (id >= 0) {
+        const int iy = w.y0 + (src >> 3), ix = xs + it * 8 + (src & 7);
         const size_t px = ((size_t)b * H + iy) * W + ix;
-        id = ids[px];
         bp[0] = bary[3 * px]; bp[1] = bary[3 * px + 1]; bp[2] = bary[3 * px + 2];
         if constexpr (SHADE) {
           const float4 g4 = reinterpret_cast<const float4 *>(grad)[((size_t)b * H + (H - 1 - iy)) * W + ix];
@@ -382,8 +430,6 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
         }
       }
     }
-    if (id >= 0 && !pixel_is_covered(id, bp)) id = -1;
-    if (__ballot_sync(0xffffffffu, id >= 0) == 0u) continue;
 
     // the dependent chain id -> triangle -> vertices.  (Base pointers pass through an opaque copy for the same
     // reason as the thread index above: hoisted out of the loop each would hold two registers throughout.)
@@ -415,20 +461,13 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
       }
     }
 
-    // Group the covered lanes by triangle and give every covered lane a ROW: the rows of one triangle
-    // are consecutive (groups ordered by their first lane).  Uncovered lanes get private keys, match
-    // nobody and own no row.  Every kPieceRows-th lane of a group heads a piece.
+    // Every covered lane's row is its lane index; every kPieceRows-th lane of a triangle heads a piece.
     const Where wg = where();
     const int lane = wg.lane;
     WarpArea &area = *wg.area;
-    const unsigned peers = __match_any_sync(0xffffffffu, id >= 0 ? id : -1 - lane);
-    const int leader = __ffs(peers) - 1;
-    const int group_size = __popc(peers), rank = __popc(peers & ((1u << lane) - 1u));
-    const int lead_size = (id >= 0 && lane == leader) ? group_size : 0;
-    const int before = warp_inclusive_scan(lead_size) - lead_size;        // rows of the groups led by lower lanes
-    const int pos = __shfl_sync(0xffffffffu, before, leader) + rank;
+    const int pos = lane;
     const bool head = id >= 0 && (rank & (kPieceRows - 1)) == 0;
-    const unsigned heads = __reduce_or_sync(0xffffffffu, head ? (1u << pos) : 0u);   // bit r: row r starts a piece
+    const unsigned heads = __ballot_sync(0xffffffffu, head);               // bit r: row r starts a piece
     const int n_pieces = __popc(heads);
 
     float gb[3] = {0.0f, 0.0f, 0.0f};
