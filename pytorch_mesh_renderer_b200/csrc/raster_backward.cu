@@ -538,38 +538,47 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
       const float4 *q = area_rows + first * ROW4 + (reducer ? j : 0);
       const int longest = __reduce_max_sync(0xffffffffu, len);      // warp-uniform trip count
       float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-      // Two rows per step: both loads are issued before the adds, so the shared-memory latency is paid once
-      // per step.  Loads and adds are predicated on the piece's own length (written as predicated PTX: left to
-      // itself the compiler branches around them and serialises load -> add per row): the warp runs the longest
+      // Two rows per step, both loads issued before the adds.  Loads and adds are predicated on the piece's own
+      // length, the entry step on the longest piece of the round (warp-uniform): the warp runs the longest
       // piece's steps exactly once and short pieces cost no shared-memory wavefronts for rows they do not have.
+      // ONE block of PTX: as C++ (conditional loads, accumulators through "+f" constraints of one asm per row)
+      // every step carried eight register moves and a convergence barrier around its loads, 26 instructions
+      // where 12 do the work.
       static_assert(kPieceRows == 16, "the steps below are written for pieces of up to 16 rows");
-#define PMR_ADD_ROW(k, v)                                                                                  \
-  asm("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %4, %5;\n\t@p add.rn.f32 %0, %0, %6;\n\t@p add.rn.f32 %1, %1, %7;\n\t" \
-      "@p add.rn.f32 %2, %2, %8;\n\t@p add.rn.f32 %3, %3, %9;\n\t}"                                       \
-      : "+f"(acc0), "+f"(acc1), "+f"(acc2), "+f"(acc3)                                                     \
-      : "r"(len), "n"(k), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
-#define PMR_TWO_ROWS(k)                                                                   \
-  {                                                                                       \
-    float4 v0, v1;                                                                        \
-    asm("" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w));   /* any value: unused when the row is absent */ \
-    asm("" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w));                             \
-    if ((k) < len) v0 = q[(k) * ROW4];                                                    \
-    if ((k) + 1 < len) v1 = q[((k) + 1) * ROW4];                                          \
-    PMR_ADD_ROW(k, v0)                                                                    \
-    PMR_ADD_ROW((k) + 1, v1)                                                              \
-  }
-      if (longest > 8) {
-        if (longest > 14) PMR_TWO_ROWS(14)
-        if (longest > 12) PMR_TWO_ROWS(12)
-        if (longest > 10) PMR_TWO_ROWS(10)
-        PMR_TWO_ROWS(8)
+      {
+        const unsigned q_at = (unsigned)__cvta_generic_to_shared(q);
+#define PMR_STEP(K, K1, OA, OB)                                                             \
+  "S" #K ":\n\t"                                                                            \
+  "setp.gt.s32 q0, %4, " #K ";\n\t"                                                         \
+  "setp.gt.s32 q1, %4, " #K1 ";\n\t"                                                        \
+  "@q0 ld.shared.v4.f32 {a0, a1, a2, a3}, [%6+" OA "];\n\t"                                 \
+  "@q1 ld.shared.v4.f32 {b0, b1, b2, b3}, [%6+" OB "];\n\t"                                 \
+  "@q0 add.rn.f32 %0, %0, a0;\n\t@q0 add.rn.f32 %1, %1, a1;\n\t"                            \
+  "@q0 add.rn.f32 %2, %2, a2;\n\t@q0 add.rn.f32 %3, %3, a3;\n\t"                            \
+  "@q1 add.rn.f32 %0, %0, b0;\n\t@q1 add.rn.f32 %1, %1, b1;\n\t"                            \
+  "@q1 add.rn.f32 %2, %2, b2;\n\t@q1 add.rn.f32 %3, %3, b3;\n\t"
+        asm volatile(
+            "{\n\t.reg .pred p, q0, q1;\n\t.reg .f32 a0, a1, a2, a3, b0, b1, b2, b3;\n\t"
+            "setp.lt.s32 p, %5, 3;\n\t@p bra.uni S0;\n\t"
+            "setp.lt.s32 p, %5, 5;\n\t@p bra.uni S2;\n\t"
+            "setp.lt.s32 p, %5, 7;\n\t@p bra.uni S4;\n\t"
+            "setp.lt.s32 p, %5, 9;\n\t@p bra.uni S6;\n\t"
+            "setp.lt.s32 p, %5, 11;\n\t@p bra.uni S8;\n\t"
+            "setp.lt.s32 p, %5, 13;\n\t@p bra.uni S10;\n\t"
+            "setp.lt.s32 p, %5, 15;\n\t@p bra.uni S12;\n\t"
+            PMR_STEP(14, 15, "%21", "%22") PMR_STEP(12, 13, "%19", "%20") PMR_STEP(10, 11, "%17", "%18")
+            PMR_STEP(8, 9, "%15", "%16") PMR_STEP(6, 7, "%13", "%14") PMR_STEP(4, 5, "%11", "%12")
+            PMR_STEP(2, 3, "%9", "%10") PMR_STEP(0, 1, "%7", "%8")
+            "}"
+            : "+f"(acc0), "+f"(acc1), "+f"(acc2), "+f"(acc3)
+            : "r"(len), "r"(longest), "r"(q_at),
+              "n"(0 * ROW4 * 16), "n"(1 * ROW4 * 16), "n"(2 * ROW4 * 16), "n"(3 * ROW4 * 16), "n"(4 * ROW4 * 16),
+              "n"(5 * ROW4 * 16), "n"(6 * ROW4 * 16), "n"(7 * ROW4 * 16), "n"(8 * ROW4 * 16), "n"(9 * ROW4 * 16),
+              "n"(10 * ROW4 * 16), "n"(11 * ROW4 * 16), "n"(12 * ROW4 * 16), "n"(13 * ROW4 * 16),
+              "n"(14 * ROW4 * 16), "n"(15 * ROW4 * 16)
+            : "memory");
+#undef PMR_STEP
       }
-      if (longest > 6) PMR_TWO_ROWS(6)
-      if (longest > 4) PMR_TWO_ROWS(4)
-      if (longest > 2) PMR_TWO_ROWS(2)
-      PMR_TWO_ROWS(0)
-#undef PMR_TWO_ROWS
-#undef PMR_ADD_ROW
       // A triangle with more than kPieceRows pixels in the block was cut into several pieces: the sums of the
       // pieces that share this round are added up (highest slot first) so that the triangle costs one set of
       // atomics, not one per piece -- what matters when few vertices take all the traffic (large triangles).
