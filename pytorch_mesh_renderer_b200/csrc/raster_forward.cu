@@ -705,6 +705,7 @@ struct ScatterWarpSmem {
   float4 r0[32], r1[32], r2[32], r3[32];     // setup records of the warp's 32 triangles (planes as in TileSmem)
   int2 origin[32];                           // left, bottom of each triangle's pixel box
   unsigned short segs[kScatterSegCap];       // slot | dy << 5 | dx << 9 | width << 13
+  unsigned char spans[kSmallBox][32];        // per box row and triangle: first candidate column | (columns - 1) << 4, 0xff: none
   unsigned short hits[160];                  // queue of inside pixels: slot | dy << 5 | x offset << 9
 };
 
@@ -740,7 +741,38 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
         sm.r2[lane] = make_float4(m[6], m[7], m[8], p1.z);
         sm.r3[lane] = make_float4(p2.z, p0.w, p1.w, p2.w);
         sm.origin[lane] = make_int2(box.left, box.bottom);
-        n_seg = bh * ((bw + 3) >> 2);
+        // Candidate columns of every box row.  A pixel passes the inside test only if all three edge values,
+        // evaluated in fp32 as K.cpp:93-98 does, are >= 0; the fp32 value of edge i differs from the exact
+        // a*x + b*y + c by at most 2^-22 * (|a| + |b| + |c|) =: d (pixel centres lie in [-1, 1]).  Along a row
+        // the exact value is linear in x, so the pixels that can pass lie on one side of the crossing
+        // x = -(b*y + c) / a, shifted by d / |a|.  An edge bounds the row only when that shift (and the rounding
+        // of this very computation, of the same size) is below 1/64 of a pixel -- |a| >= 2^-16 * W/2 * (|a| +
+        // |b| + |c|) -- and the span is widened by a quarter pixel on both sides; nearly horizontal edges bound
+        // nothing.  On c2 (boxes of 6.3 x 6.3 pixels around triangles of 7.7) this halves the row segments.
+        float cross[3];                        // -1 / a of the edges that bound rows, else 0
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float mag = fabsf(m[3 * i]) + fabsf(m[3 * i + 1]) + fabsf(m[3 * i + 2]);
+          cross[i] = fabsf(m[3 * i]) >= 1.52587890625e-5f * half_w * mag ? -1.0f / m[3 * i] : 0.0f;
+        }
+        const float left_f = (float)box.left, last_f = (float)(bw - 1);
+        for (int dy = 0; dy < bh; ++dy) {
+          const float y = __ldg(cy + box.bottom + dy);
+          float x_lo = -2.0f, x_hi = 2.0f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float x = (m[3 * i + 1] * y + m[3 * i + 2]) * cross[i];      // NaN (0 * inf): ignored by fmaxf / fminf
+            if (cross[i] < 0.0f) x_lo = fmaxf(x_lo, x);                        // a > 0: inside to the right
+            if (cross[i] > 0.0f) x_hi = fminf(x_hi, x);
+          }
+          // pixel k has its centre at (k + 0.5) / half_w - 1
+          const float k_lo = ceilf((x_lo + 1.0f) * half_w - 0.75f), k_hi = floorf((x_hi + 1.0f) * half_w - 0.25f);
+          const int d_lo = (int)fminf(fmaxf(k_lo - left_f, 0.0f), 16.0f);
+          const int d_hi = (int)fmaxf(fminf(k_hi - left_f, last_f), -1.0f);
+          const int columns = d_hi - d_lo + 1;
+          sm.spans[dy][lane] = columns > 0 ? (unsigned char)(d_lo | ((columns - 1) << 4)) : (unsigned char)0xff;
+          if (columns > 0) n_seg += (columns + 3) >> 2;
+        }
       } else {
         big_box = pack_box(box);
         is_large = true;
@@ -788,12 +820,14 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
     const bool fits = mine > 0 && seg_end <= kScatterSegCap;
     if (fits) {
       int k = seg_end - mine;
-      const int per_row = (bw + 3) >> 2;               // 1..4 segments per row
       for (int dy = 0; dy < bh; ++dy) {
+        const unsigned span = sm.spans[dy][lane];
+        if (span == 0xffu) continue;
         const unsigned head = lane | (dy << 5);
+        const int first = span & 15u, columns = (span >> 4) + 1, per_row = (columns + 3) >> 2;   // 1..4 segments
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (q < per_row) sm.segs[k + q] = (unsigned short)(head | ((4 * q) << 9) | (min(4, bw - 4 * q) << 13));
+          if (q < per_row) sm.segs[k + q] = (unsigned short)(head | ((first + 4 * q) << 9) | (min(4, columns - 4 * q) << 13));
         k += per_row;
       }
     }
