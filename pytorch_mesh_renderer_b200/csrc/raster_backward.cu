@@ -17,12 +17,12 @@
 //
 // Per-pixel arithmetic is shared with the forward pass (raster_math.cuh) and follows the
 // reference op for op; compile with -fmad=false.
-#include <cuda.h>
 #include <stddef.h>
 
 #include "pmr_internal.cuh"
 #include "raster_math.cuh"
 #include "shade_math.cuh"
+#include "tensor_maps.cuh"
 
 namespace pmr {
 
@@ -231,17 +231,6 @@ struct BlockRows {
 
 __device__ __forceinline__ void red_add(float *addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
-}
-
-__device__ __forceinline__ bool elect_one() {
-  unsigned pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
 // The per-block inputs as tensor maps: ids [B*H][W] box 8x4, barycentrics [B*H][3W] box 24x4, gradient
@@ -969,40 +958,6 @@ static int strip_blocks_for(const Context *ctx, int W, int H, int B) {
 
 static dim3 strip_grid(int W, int H, int B, int strip) {
   return dim3((W + 8 * strip - 1) / (8 * strip), (H + 4 * kStripWarps - 1) / (4 * kStripWarps), B);
-}
-
-// cuTensorMapEncodeTiled through the runtime (the library does not link libcuda).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult found;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &found) != cudaSuccess ||
-        found != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    cudaGetLastError();
-    return (EncodeTiledFn)p;
-  }();
-  return fn;
-}
-
-// Tensor map over a dense [rows][inner] array of 4-byte elements with boxes of 4 rows.  False when the
-// array cannot be described (base or row pitch not 16-byte aligned, box too wide, no driver entry point).
-static bool make_block_map(CUtensorMap *map, CUtensorMapDataType type, const void *base, long long inner,
-                           long long rows, int box_inner) {
-  EncodeTiledFn fn = encode_tiled();
-  if (fn == nullptr || base == nullptr || ((uintptr_t)base & 15) != 0 || (inner * 4) % 16 != 0 || box_inner > 256 ||
-      inner <= 0 || rows <= 0 || inner >= (1LL << 32) || rows >= (1LL << 32))
-    return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
-  const cuuint64_t pitch[1] = {(cuuint64_t)inner * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)box_inner, 4};
-  const cuuint32_t step[2] = {1, 1};
-  return fn(map, type, 2, const_cast<void *>(base), dims, pitch, box, step, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int make_block_maps(const Context *ctx, BlockMaps *maps, const int32_t *ids, const float *bary, const float *grad,

@@ -34,6 +34,7 @@
 #include "pmr_internal.cuh"
 #include "raster_math.cuh"
 #include "shade_math.cuh"
+#include "tensor_maps.cuh"
 
 namespace pmr {
 
@@ -161,13 +162,18 @@ __device__ __forceinline__ void bulk_store_commit_and_wait() {
 // the bulk-copy engine (one elected lane issues one cp.async.bulk per block row: 96 B and 32*A B), which
 // takes the copy loops off the instruction-issue-bound SMs; edge / unaligned blocks use vector or
 // scalar stores.
+// Tensor maps of the outputs that are staged: barycentrics [B*H][3W] box 24 x 4, image [B*H][A*W] box 8A x 4.
+struct OutputMaps {
+  CUtensorMap bary, image;
+};
+
 template <int A_STATIC>
 __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, int blk_y0, int W, int H, int V,
                                                const Fragment &best, const int32_t *__restrict__ tris,
                                                const float *__restrict__ attrs, const float *__restrict__ background,
                                                int A, int32_t *__restrict__ out_ids, float *__restrict__ out_bary,
                                                float *__restrict__ out_z, float *__restrict__ out_image,
-                                               const float *corners = nullptr) {
+                                               const float *corners = nullptr, const OutputMaps *maps = nullptr) {
   // `corners`: the winner's 3*A corner attributes already in registers ([corner][attribute]), or
   // nullptr to gather them here.
   const int lane = threadIdx.x & 31;
@@ -222,6 +228,21 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
     }
   }
   __syncwarp();
+  // `maps` (stage 128-byte aligned): the two staged arrays leave as ONE tensor store each, issued by one
+  // lane; columns beyond the image are clipped by the copy engine.  The eight per-row bulk copies below cost
+  // ~130 warp instructions per block (every lane's copy is issued in turn through uniform registers), more
+  // than a quarter of the resolve kernel.
+  if (maps != nullptr && vec_ok && rows == 4 && (out_image == nullptr || staged)) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy reads
+    __syncwarp();
+    if (elect_one()) {
+      const unsigned stage_at = (unsigned)__cvta_generic_to_shared(stage);
+      tma_store_2d(&maps->bary, 3 * blk_x0, b * H + blk_y0, stage_at);
+      if (out_image != nullptr) tma_store_2d(&maps->image, A * blk_x0, b * H + blk_y0, stage_at + 4u * (unsigned)kImageAt);
+      tma_store_wait_read();
+    }
+    return;
+  }
   if (bulk) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy reads
     __syncwarp();
@@ -749,6 +770,8 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
         // of this very computation, of the same size) is below 1/64 of a pixel -- |a| >= 2^-16 * W/2 * (|a| +
         // |b| + |c|) -- and the span is widened by a quarter pixel on both sides; nearly horizontal edges bound
         // nothing.  On c2 (boxes of 6.3 x 6.3 pixels around triangles of 7.7) this halves the row segments.
+        // (Taking the rows of boxes of <= 4 columns whole -- one segment per row whatever the span -- was
+        // measured: c3 0.731 -> 0.717 ms, but c2 0.326 -> 0.332 and c4 1.695 -> 1.741: empty rows matter more.)
         float cross[3];                        // -1 / a of the edges that bound rows, else 0
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -893,7 +916,8 @@ constexpr int kResolveWarps = 8;
 // (shade_math.cuh) and only RGBA is written, rows flipped as phong_shader returns them (render.py:382-386).
 template <int A_STATIC, bool SHADE>
 __global__ void __launch_bounds__(kResolveWarps * 32, SHADE ? 5 : 8)
-resolve_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int W, int H,
+resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma,
+               const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int W, int H,
                const float *__restrict__ centers,
                const unsigned long long *__restrict__ keys,
                int32_t *__restrict__ out_ids, float *__restrict__ out_bary, float *__restrict__ out_z,
@@ -901,7 +925,7 @@ resolve_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris
                float *__restrict__ out_image, const float *__restrict__ light_positions,
                const float *__restrict__ light_intensities, const float *__restrict__ ambient, int L,
                float4 *__restrict__ out_rgba) {
-  __shared__ __align__(16) float stage_all[kResolveWarps][32 * 16];
+  __shared__ __align__(128) float stage_all[kResolveWarps][32 * 16];
   __shared__ Lights lights;
   const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -926,11 +950,11 @@ resolve_kernel(const float *__restrict__ verts, const int32_t *__restrict__ tris
   // instead of 38 cost more occupancy than the shorter dependency chain gained: 0.355 -> 0.411 ms.)
   if (!SHADE) {
     block_epilogue<A_STATIC>(stage_all[warp], b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
-                             out_ids, out_bary, out_z, out_image);
+                             out_ids, out_bary, out_z, out_image, nullptr, use_tma ? &maps : nullptr);
     return;
   }
   block_epilogue<0>(stage_all[warp], b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
-                    out_ids, out_bary, out_z, nullptr);
+                    out_ids, out_bary, out_z, nullptr, nullptr, use_tma ? &maps : nullptr);
   if (ix < W && iy < H) {
     // the same interpolation as block_epilogue (rast.py:118-150), into registers
     float px[9];
@@ -1083,13 +1107,20 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
   {
     StageScope timed(ctx, PMR_STAGE_RESOLVE, stream);
     dim3 grid((W + 15) / 16, (H + 2 * kResolveWarps - 1) / (2 * kResolveWarps), B);
+    // the staged outputs as tensor maps (PMR_NO_TMA=1 or an array the copy engine cannot describe: per-row copies)
+    OutputMaps maps;
+    const bool image_staged = shade == nullptr && image != nullptr && (A == 4 || A == 9 || A == 12 || A == 13);
+    const int use_tma = !ctx->no_tma && (H & 3) == 0 &&
+                        make_block_map(&maps.bary, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, bary, 3LL * W, (long long)B * H, 24) &&
+                        (!image_staged || make_block_map(&maps.image, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, image,
+                                                         (long long)A * W, (long long)B * H, 8 * A));
 #define PMR_RESOLVE(AS)                                                                                          \
-  resolve_kernel<AS, false><<<grid, kResolveWarps * 32, 0, stream>>>(verts, tris, V, W, H, centers, keys, ids,   \
-                                                              bary, z, attrs, bg, A, image, nullptr, nullptr,    \
-                                                              nullptr, 0, nullptr)
+  resolve_kernel<AS, false><<<grid, kResolveWarps * 32, 0, stream>>>(maps, use_tma, verts, tris, V, W, H, centers, \
+                                                              keys, ids, bary, z, attrs, bg, A, image, nullptr,  \
+                                                              nullptr, nullptr, 0, nullptr)
     if (shade != nullptr)
       resolve_kernel<9, true><<<grid, kResolveWarps * 32, 0, stream>>>(
-          verts, tris, V, W, H, centers, keys, ids, bary, z, attrs, bg, 9, nullptr, shade->light_positions,
+          maps, use_tma, verts, tris, V, W, H, centers, keys, ids, bary, z, attrs, bg, 9, nullptr, shade->light_positions,
           shade->light_intensities, shade->ambient, shade->L, reinterpret_cast<float4 *>(shade->rgba));
     else if (image == nullptr) PMR_RESOLVE(0);
     else if (A == 4) PMR_RESOLVE(4);
