@@ -162,9 +162,10 @@ __device__ __forceinline__ void bulk_store_commit_and_wait() {
 // the bulk-copy engine (one elected lane issues one cp.async.bulk per block row: 96 B and 32*A B), which
 // takes the copy loops off the instruction-issue-bound SMs; edge / unaligned blocks use vector or
 // scalar stores.
-// Tensor maps of the outputs that are staged: barycentrics [B*H][3W] box 24 x 4, image [B*H][A*W] box 8A x 4.
+// Tensor maps of the outputs that are staged: barycentrics [B*H][3W] box 24 x 4, image [B*H][A*W] box 8A x 4;
+// and of the resolve kernel's input, the depth keys as [B*H][2W] 32-bit words, box 64 x 4 (a strip of 32 x 4 pixels).
 struct OutputMaps {
-  CUtensorMap bary, image;
+  CUtensorMap bary, image, keys;
 };
 
 template <int A_STATIC>
@@ -173,7 +174,8 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
                                                const float *__restrict__ attrs, const float *__restrict__ background,
                                                int A, int32_t *__restrict__ out_ids, float *__restrict__ out_bary,
                                                float *__restrict__ out_z, float *__restrict__ out_image,
-                                               const float *corners = nullptr, const OutputMaps *maps = nullptr) {
+                                               const float *corners = nullptr, const OutputMaps *maps = nullptr,
+                                               bool defer_wait = false) {
   // `corners`: the winner's 3*A corner attributes already in registers ([corner][attribute]), or
   // nullptr to gather them here.
   const int lane = threadIdx.x & 31;
@@ -235,11 +237,13 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
   if (maps != nullptr && vec_ok && rows == 4 && (out_image == nullptr || staged)) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy reads
     __syncwarp();
-    if (elect_one()) {
+    // defer_wait: the caller (lane 0) waits for the reads before the stage is written again or the warp exits
+    if (lane == 0) {
       const unsigned stage_at = (unsigned)__cvta_generic_to_shared(stage);
       tma_store_2d(&maps->bary, 3 * blk_x0, b * H + blk_y0, stage_at);
       if (out_image != nullptr) tma_store_2d(&maps->image, A * blk_x0, b * H + blk_y0, stage_at + 4u * (unsigned)kImageAt);
-      tma_store_wait_read();
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (!defer_wait) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     return;
   }
@@ -910,12 +914,20 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
 // ---------------------------------------------------------------------------------------------
 
 constexpr int kResolveWarps = 8;
+constexpr int kResolveStrip = 4;             // blocks of 8 x 4 pixels a warp resolves, left to right
 
+// One warp per strip of kResolveStrip blocks, 2 x 4 strips per CTA (64 x 16 pixels).  With tensor maps the strip's
+// depth keys (32 x 4 pixels, 1 KB) arrive by ONE bulk tensor copy issued when the warp starts: a warp that
+// resolves a single block spends a fifth of its life waiting for its first load (ncu, profiles/r02: 20 % of the
+// stall samples on the key), here that wait is paid once per strip and the tensor stores of block i drain while
+// block i + 1 is computed.  40 registers, 6 CTAs per SM: at 8 CTAs (32 registers) the loop state spills and the
+// kernel takes 0.385 ms instead of 0.279 (c2); 5 / 4 CTAs: 0.296 / 0.312.  Against one block per warp (0.286 ms,
+// 202 M instructions) the strips cost 35 M instructions and win 2 % on c2 / c4, lose 4 % on c5.
 // SHADE: the render path (render.py:198-228 without specular colours).  The nine interpolated channels
 // [normal, world position, diffuse colour] of a pixel never leave the registers: they are lit right here
 // (shade_math.cuh) and only RGBA is written, rows flipped as phong_shader returns them (render.py:382-386).
-template <int A_STATIC, bool SHADE>
-__global__ void __launch_bounds__(kResolveWarps * 32, SHADE ? 5 : 8)
+template <int A_STATIC, bool SHADE, int MIN_CTAS = (SHADE ? 5 : 6)>
+__global__ void __launch_bounds__(kResolveWarps * 32, MIN_CTAS)
 resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma,
                const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int W, int H,
                const float *__restrict__ centers,
@@ -926,56 +938,98 @@ resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma,
                const float *__restrict__ light_intensities, const float *__restrict__ ambient, int L,
                float4 *__restrict__ out_rgba) {
   __shared__ __align__(128) float stage_all[kResolveWarps][32 * 16];
+  __shared__ __align__(128) unsigned long long keys_all[kResolveWarps][4 * 8 * kResolveStrip];
+  __shared__ unsigned long long ready_all[kResolveWarps];
   __shared__ Lights lights;
   const int A = A_STATIC > 0 ? A_STATIC : A_dyn;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // the CTA covers a 16x16 pixel tile: 2 blocks across, 4 down
   const int b = blockIdx.z;
   if (SHADE) load_lights(lights, light_positions, light_intensities, ambient, b, L);     // block barrier inside
-  const int blk_x0 = (blockIdx.x * 2 + (warp & 1)) * 8, blk_y0 = (blockIdx.y * (kResolveWarps / 2) + (warp >> 1)) * 4;
-  if (blk_x0 >= W || blk_y0 >= H) return;
-  const int ix = blk_x0 + (lane & 7), iy = blk_y0 + (lane >> 3);
-  Fragment best;
-  fragment_clear(best);
-  if (ix < W && iy < H) {
-    const unsigned long long key = keys[((size_t)b * H + iy) * W + ix];
+  const int x0 = (blockIdx.x * 2 + (warp & 1)) * (8 * kResolveStrip), y0 = (blockIdx.y * (kResolveWarps / 2) + (warp >> 1)) * 4;
+  if (x0 >= W || y0 >= H) return;
+  const int n_blocks = min(kResolveStrip, (W - x0 + 7) >> 3);
+  const int iy = y0 + (lane >> 3);
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&ready_all[warp]);
+  if (use_tma) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)sizeof(keys_all[0])) : "memory");
+      tma_load_2d((unsigned)__cvta_generic_to_shared(keys_all[warp]), &maps.keys, 2 * x0, b * H + y0, bar);
+    }
+    __syncwarp();
+  }
+  const unsigned tid_kept = threadIdx.x;
+  for (int it = 0; it < n_blocks; ++it) {
+    // what depends on the thread only is re-derived from an opaque copy of its index: kept in registers across
+    // the loop it pushes the per-pixel arithmetic into spills
+    // (the CTA's coordinates too: 24 bytes of spills at 40 registers otherwise)
+    unsigned tid = tid_kept, b_now, cta_x, cta_y;
+    asm volatile("" : "+r"(tid));
+    asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(b_now));
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta_x));
+    asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(cta_y));
+    const int b = (int)b_now;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int x0 = (cta_x * 2 + (warp & 1)) * (8 * kResolveStrip), y0 = (cta_y * (kResolveWarps / 2) + (warp >> 1)) * 4;
+    const int iy = y0 + (lane >> 3);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&ready_all[warp]);
+    const int blk_x0 = x0 + 8 * it, ix = blk_x0 + (lane & 7);
+    const bool in_image = ix < W && iy < H;
+    unsigned long long key = kEmptyKey;
+    if (use_tma) {
+      if (it == 0) {
+        unsigned done = 0;
+        while (!done) {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        }
+      }
+      if (in_image) key = keys_all[warp][(lane >> 3) * (8 * kResolveStrip) + it * 8 + (lane & 7)];   // (columns beyond W: zero fill)
+    } else if (in_image) {
+      key = keys[((size_t)b * H + iy) * W + ix];
+    }
+    Fragment best;
+    fragment_clear(best);
     if (key != kEmptyKey) {
       const int t = depth_key_id(key);
       float4 p0, p1, p2;
       load_triangle(verts + (size_t)b * V * 4, tris, t, p0, p1, p2);
       evaluate_winner(p0, p1, p2, __ldg(centers + ix), __ldg(centers + W + iy), t, best);
     }
-  }
-  // (Gathering the 3*A corner attributes here, together with the vertices, was measured: 60 registers
-  // instead of 38 cost more occupancy than the shorter dependency chain gained: 0.355 -> 0.411 ms.)
-  if (!SHADE) {
-    block_epilogue<A_STATIC>(stage_all[warp], b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
-                             out_ids, out_bary, out_z, out_image, nullptr, use_tma ? &maps : nullptr);
-    return;
-  }
-  block_epilogue<0>(stage_all[warp], b, blk_x0, blk_y0, W, H, V, best, tris, attrs, background, A,
-                    out_ids, out_bary, out_z, nullptr, nullptr, use_tma ? &maps : nullptr);
-  if (ix < W && iy < H) {
-    // the same interpolation as block_epilogue (rast.py:118-150), into registers
-    float px[9];
-    if (best.id < 0) {
-#pragma unroll
-      for (int a = 0; a < 9; ++a) px[a] = __ldg(background + a);
-    } else {
-      const float alpha = coverage_alpha(best.b0, best.b1, best.b2);
-      const float one_minus = 1.0f - alpha;
-      const float *at = attrs + (size_t)b * V * 9;
-      const float *c0 = at + (size_t)__ldg(tris + 3 * (size_t)best.id + 0) * 9;
-      const float *c1 = at + (size_t)__ldg(tris + 3 * (size_t)best.id + 1) * 9;
-      const float *c2 = at + (size_t)__ldg(tris + 3 * (size_t)best.id + 2) * 9;
-#pragma unroll
-      for (int a = 0; a < 9; ++a) {
-        const float img = __ldg(c0 + a) * best.b0 + __ldg(c1 + a) * best.b1 + __ldg(c2 + a) * best.b2;
-        px[a] = alpha * img + one_minus * __ldg(background + a);
-      }
+    // (Gathering the 3*A corner attributes here, together with the vertices, was measured: 60 registers
+    // instead of 38 cost more occupancy than the shorter dependency chain gained: 0.355 -> 0.411 ms.)
+    if (use_tma && it > 0) {               // the previous block's tensor stores have read the stage
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
     }
-    out_rgba[((size_t)b * H + (H - 1 - iy)) * W + ix] = shade_diffuse_pixel(px, px + 3, px + 6, lights, L, ambient != nullptr);
+    block_epilogue<SHADE ? 0 : A_STATIC>(stage_all[warp], b, blk_x0, y0, W, H, V, best, tris, attrs, background, A,
+                                         out_ids, out_bary, out_z, SHADE ? nullptr : out_image, nullptr,
+                                         use_tma ? &maps : nullptr, true);
+    if (SHADE && in_image) {
+      // the same interpolation as block_epilogue (rast.py:118-150), into registers
+      float px[9];
+      if (best.id < 0) {
+#pragma unroll
+        for (int a = 0; a < 9; ++a) px[a] = __ldg(background + a);
+      } else {
+        const float alpha = coverage_alpha(best.b0, best.b1, best.b2);
+        const float one_minus = 1.0f - alpha;
+        const float *at = attrs + (size_t)b * V * 9;
+        const float *c0 = at + (size_t)__ldg(tris + 3 * (size_t)best.id + 0) * 9;
+        const float *c1 = at + (size_t)__ldg(tris + 3 * (size_t)best.id + 1) * 9;
+        const float *c2 = at + (size_t)__ldg(tris + 3 * (size_t)best.id + 2) * 9;
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+          const float img = __ldg(c0 + a) * best.b0 + __ldg(c1 + a) * best.b1 + __ldg(c2 + a) * best.b2;
+          px[a] = alpha * img + one_minus * __ldg(background + a);
+        }
+      }
+      out_rgba[((size_t)b * H + (H - 1 - iy)) * W + ix] = shade_diffuse_pixel(px, px + 3, px + 6, lights, L, ambient != nullptr);
+    }
+    if (!use_tma) __syncwarp();            // the stage is rewritten by the next block
   }
+  if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // Standalone interpolation (rast.py:118-150) from existing id / barycentric buffers.
@@ -1106,11 +1160,12 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
   if (rc) return rc;
   {
     StageScope timed(ctx, PMR_STAGE_RESOLVE, stream);
-    dim3 grid((W + 15) / 16, (H + 2 * kResolveWarps - 1) / (2 * kResolveWarps), B);
+    dim3 grid((W + 16 * kResolveStrip - 1) / (16 * kResolveStrip), (H + 2 * kResolveWarps - 1) / (2 * kResolveWarps), B);
     // the staged outputs as tensor maps (PMR_NO_TMA=1 or an array the copy engine cannot describe: per-row copies)
     OutputMaps maps;
     const bool image_staged = shade == nullptr && image != nullptr && (A == 4 || A == 9 || A == 12 || A == 13);
     const int use_tma = !ctx->no_tma && (H & 3) == 0 &&
+                        make_block_map(&maps.keys, CU_TENSOR_MAP_DATA_TYPE_UINT32, keys, 2LL * W, (long long)B * H, 16 * kResolveStrip) &&
                         make_block_map(&maps.bary, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, bary, 3LL * W, (long long)B * H, 24) &&
                         (!image_staged || make_block_map(&maps.image, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, image,
                                                          (long long)A * W, (long long)B * H, 8 * A));
