@@ -914,7 +914,7 @@ scatter_small_kernel(const float *__restrict__ verts, const int32_t *__restrict_
 // ---------------------------------------------------------------------------------------------
 
 constexpr int kResolveWarps = 8;
-constexpr int kResolveStrip = 4;             // blocks of 8 x 4 pixels a warp resolves, left to right
+constexpr int kResolveStrip = 4;             // most blocks of 8 x 4 pixels a warp resolves, left to right (fewer for small batches)
 
 // One warp per strip of kResolveStrip blocks, 2 x 4 strips per CTA (64 x 16 pixels).  With tensor maps the strip's
 // depth keys (32 x 4 pixels, 1 KB) arrive by ONE bulk tensor copy issued when the warp starts: a warp that
@@ -928,7 +928,7 @@ constexpr int kResolveStrip = 4;             // blocks of 8 x 4 pixels a warp re
 // (shade_math.cuh) and only RGBA is written, rows flipped as phong_shader returns them (render.py:382-386).
 template <int A_STATIC, bool SHADE, int MIN_CTAS = (SHADE ? 5 : 6)>
 __global__ void __launch_bounds__(kResolveWarps * 32, MIN_CTAS)
-resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma,
+resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma, int strip_blocks,
                const float *__restrict__ verts, const int32_t *__restrict__ tris, int V, int W, int H,
                const float *__restrict__ centers,
                const unsigned long long *__restrict__ keys,
@@ -945,16 +945,16 @@ resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z;
   if (SHADE) load_lights(lights, light_positions, light_intensities, ambient, b, L);     // block barrier inside
-  const int x0 = (blockIdx.x * 2 + (warp & 1)) * (8 * kResolveStrip), y0 = (blockIdx.y * (kResolveWarps / 2) + (warp >> 1)) * 4;
+  const int x0 = (blockIdx.x * 2 + (warp & 1)) * (8 * strip_blocks), y0 = (blockIdx.y * (kResolveWarps / 2) + (warp >> 1)) * 4;
   if (x0 >= W || y0 >= H) return;
-  const int n_blocks = min(kResolveStrip, (W - x0 + 7) >> 3);
+  const int n_blocks = min(strip_blocks, (W - x0 + 7) >> 3);
   const int iy = y0 + (lane >> 3);
   const unsigned bar = (unsigned)__cvta_generic_to_shared(&ready_all[warp]);
   if (use_tma) {
     if (lane == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)sizeof(keys_all[0])) : "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(256 * strip_blocks)) : "memory");
       tma_load_2d((unsigned)__cvta_generic_to_shared(keys_all[warp]), &maps.keys, 2 * x0, b * H + y0, bar);
     }
     __syncwarp();
@@ -971,7 +971,7 @@ resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma,
     asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(cta_y));
     const int b = (int)b_now;
     const int lane = tid & 31, warp = tid >> 5;
-    const int x0 = (cta_x * 2 + (warp & 1)) * (8 * kResolveStrip), y0 = (cta_y * (kResolveWarps / 2) + (warp >> 1)) * 4;
+    const int x0 = (cta_x * 2 + (warp & 1)) * (8 * strip_blocks), y0 = (cta_y * (kResolveWarps / 2) + (warp >> 1)) * 4;
     const int iy = y0 + (lane >> 3);
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&ready_all[warp]);
     const int blk_x0 = x0 + 8 * it, ix = blk_x0 + (lane & 7);
@@ -985,7 +985,7 @@ resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma,
                        : "=r"(done) : "r"(bar), "r"(0u) : "memory");
         }
       }
-      if (in_image) key = keys_all[warp][(lane >> 3) * (8 * kResolveStrip) + it * 8 + (lane & 7)];   // (columns beyond W: zero fill)
+      if (in_image) key = keys_all[warp][(lane >> 3) * (8 * strip_blocks) + it * 8 + (lane & 7)];   // (columns beyond W: zero fill)
     } else if (in_image) {
       key = keys[((size_t)b * H + iy) * W + ix];
     }
@@ -1160,22 +1160,27 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
   if (rc) return rc;
   {
     StageScope timed(ctx, PMR_STAGE_RESOLVE, stream);
-    dim3 grid((W + 16 * kResolveStrip - 1) / (16 * kResolveStrip), (H + 2 * kResolveWarps - 1) / (2 * kResolveWarps), B);
+    // strips of four blocks unless that leaves fewer than a dozen waves of CTAs (c4 at 32 views per GPU: 9): the
+    // last, partly filled wave would show
+    int strip = kResolveStrip;
+    const long long cta_rows = (long long)((H + 2 * kResolveWarps - 1) / (2 * kResolveWarps)) * B;
+    while (strip > 1 && cta_rows * ((W + 16 * strip - 1) / (16 * strip)) < 12LL * 6 * ctx->sm_count) strip >>= 1;
+    dim3 grid((W + 16 * strip - 1) / (16 * strip), (H + 2 * kResolveWarps - 1) / (2 * kResolveWarps), B);
     // the staged outputs as tensor maps (PMR_NO_TMA=1 or an array the copy engine cannot describe: per-row copies)
     OutputMaps maps;
     const bool image_staged = shade == nullptr && image != nullptr && (A == 4 || A == 9 || A == 12 || A == 13);
     const int use_tma = !ctx->no_tma && (H & 3) == 0 &&
-                        make_block_map(&maps.keys, CU_TENSOR_MAP_DATA_TYPE_UINT32, keys, 2LL * W, (long long)B * H, 16 * kResolveStrip) &&
+                        make_block_map(&maps.keys, CU_TENSOR_MAP_DATA_TYPE_UINT32, keys, 2LL * W, (long long)B * H, 16 * strip) &&
                         make_block_map(&maps.bary, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, bary, 3LL * W, (long long)B * H, 24) &&
                         (!image_staged || make_block_map(&maps.image, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, image,
                                                          (long long)A * W, (long long)B * H, 8 * A));
 #define PMR_RESOLVE(AS)                                                                                          \
-  resolve_kernel<AS, false><<<grid, kResolveWarps * 32, 0, stream>>>(maps, use_tma, verts, tris, V, W, H, centers, \
+  resolve_kernel<AS, false><<<grid, kResolveWarps * 32, 0, stream>>>(maps, use_tma, strip, verts, tris, V, W, H, centers, \
                                                               keys, ids, bary, z, attrs, bg, A, image, nullptr,  \
                                                               nullptr, nullptr, 0, nullptr)
     if (shade != nullptr)
       resolve_kernel<9, true><<<grid, kResolveWarps * 32, 0, stream>>>(
-          maps, use_tma, verts, tris, V, W, H, centers, keys, ids, bary, z, attrs, bg, 9, nullptr, shade->light_positions,
+          maps, use_tma, strip, verts, tris, V, W, H, centers, keys, ids, bary, z, attrs, bg, 9, nullptr, shade->light_positions,
           shade->light_intensities, shade->ambient, shade->L, reinterpret_cast<float4 *>(shade->rgba));
     else if (image == nullptr) PMR_RESOLVE(0);
     else if (A == 4) PMR_RESOLVE(4);
