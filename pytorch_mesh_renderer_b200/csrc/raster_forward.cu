@@ -1142,7 +1142,9 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
     StageScope timed(ctx, PMR_STAGE_BIN, stream);
     PMR_CUDA(ctx, cudaMemsetAsync(work_cursor, 0, (size_t)(B + 1) * sizeof(int), stream));
     // (Letting the resolve kernel clear each key it reads, to save this memset, made that kernel 5x slower:
-    // 0.31 -> 1.47 ms on c2, every load of the chain behind the store stalled; profiles/r02/SUMMARY.md.)
+    // 0.31 -> 1.47 ms on c2, every load of the chain behind the store stalled.  Storing an empty box back over
+    // each strip by one tensor store per warp, the buffer kept clean between calls: memset 0.025 -> 0.004 ms
+    // but resolve 0.279 -> 0.293: 0.6 % of the step, not worth a buffer whose state outlives the call.)
     PMR_CUDA(ctx, cudaMemsetAsync(keys, 0xff, n_pixels * sizeof(unsigned long long), stream));   // kEmptyKey
   }
   {
