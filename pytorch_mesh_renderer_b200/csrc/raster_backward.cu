@@ -404,8 +404,8 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
 #pragma unroll
           for (int a = 0; a < GC; ++a) g_local[a] = area.grad[src * GC + a];
         }
-        __syncwarp();                             // the boxes are consumed by every lane before they are refilled
-        if (it + 1 < n_blocks) fetch_block(w, it + 1);              // lands while this block is processed
+        // (The boxes are refilled further down, once these values have been USED: a load that has merely been
+        // issued can still be in the L1 queue when the copy engine's data arrives.)
       } else if (id >= 0) {
         const int iy = w.y0 + (src >> 3), ix = xs + it * 8 + (src & 7);
         const size_t px = ((size_t)b * H + iy) * W + ix;
@@ -501,6 +501,12 @@ backward_blocks_kernel(const __grid_constant__ BlockMaps maps, int use_tma,
       area.vids[pos] = make_int4(vid[0], vid[1], vid[2], 0);
     }
     __syncwarp();
+    // The boxes of the next block: requested only now, when every value read from this block's boxes has gone
+    // through the arithmetic above (the row stores could not issue before the loads had returned) -- a
+    // shared-memory load and the copy engine's write are ordered by nothing but that; issued right after
+    // the loads, a fraction of 1e-5 of the gradient entries came out wrong under load (run-to-run check,
+    // profiles/tools/run_to_run.py).  The copy still lands during the reduction below.
+    if (use_tma && it + 1 < n_blocks) fetch_block(wg, it + 1);
 
     // Reduction: SLOTS pieces per round; a lane adds its four columns over the rows of its piece and issues
     // one atomic per column.  Column e of corner k goes to d_verts[vtx_k*4 + {0,1,3}[e]] for e < 3 and to

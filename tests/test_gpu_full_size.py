@@ -6,7 +6,8 @@ The whole batch runs through the CUDA path; parity is then established two ways:
   * size-independent properties over the whole batch: id range, barycentric sums, clear values,
     fused image == standalone interpolation of the produced buffers, run-to-run determinism, exact
     linearity of the ORDERED backward under scaling by 2, ATOMIC gradients within the summation-order
-    bound of the oracle's double-accumulated yardstick.
+    bound of the oracle's double-accumulated yardstick, and the full-batch ATOMIC backward (twice) against
+    the full-batch ORDERED one.
 """
 import numpy as np
 import pytest
@@ -96,3 +97,14 @@ def test_full_size_config(pmr, oracle, name):
     g_all = torch.randn((B, H, W, A), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
     dv, da = ops.rasterize_interpolate_backward(g_all, clip, attrs, tris, ids, bary, "atomic")
     assert torch.isfinite(dv).all() and torch.isfinite(da).all() and not dv[..., 2].any()
+    # ... and gives the ORDERED (bit-exact) mode's sums up to the order of the additions, over the WHOLE batch and
+    # twice: under full load a backward kernel that refilled its tensor-copy boxes too early once produced a
+    # fraction of 1e-5 of the entries wrong by up to the size of the entry (never on a single image).
+    dvo, dao = ops.rasterize_interpolate_backward(g_all, clip, attrs, tris, ids, bary, "ordered")
+    for rep in range(2):
+        if rep:
+            dv, da = ops.rasterize_interpolate_backward(g_all, clip, attrs, tris, ids, bary, "atomic")
+        for mine, ref, what in ((dv, dvo, "d_vertices"), (da, dao, "d_attributes")):
+            off = (mine - ref).abs() > 1e-4 * float(ref.abs().max())
+            assert not bool(off.any()), "%s: %d entries of the atomic mode differ from the ordered mode (run %d)" % (
+                what, int(off.sum()), rep)
