@@ -22,4 +22,3 @@ run 8 peer n8_peer_graph "--no-e2e"
 run 8 nccl n8_nccl_graph "--no-e2e"
 run 4 peer n4_peer_graph "--no-e2e"
 run 2 peer n2_peer_graph "--no-e2e"
-timeout 600 python -m pytest tests/test_gpu_peer_exchange.py -m gpu -q -x 2>&1 | tail -3
