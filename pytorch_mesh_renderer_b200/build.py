@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpmr_b200.so")
 SOURCES = ["c_api.cu", "raster_forward.cu", "raster_backward.cu", "vertex_stage.cu", "shade.cu", "mesh_normals.cu", "peer_exchange.cu"]
-HEADERS = ["pmr_internal.cuh", "raster_math.cuh", "shade_math.cuh", os.path.join("..", "..", "include", "pmr_b200.h")]
+HEADERS = ["pmr_internal.cuh", "raster_math.cuh", "shade_math.cuh", "tensor_maps.cuh", os.path.join("..", "..", "include", "pmr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-extended-lambda"]
