@@ -15,15 +15,21 @@ import torch.distributed as dist
 from . import _lib
 
 
-def shard_views(n_views, rank=None, world_size=None):
-    """Contiguous slice of the view (batch) dimension owned by `rank`: range(start, stop).
+def shard_views(n_views, rank=None, world_size=None, interleaved=False):
+    """The views (batch entries) owned by `rank`, as a range: a contiguous slice range(start, stop), or with
+    `interleaved` every world_size-th view, range(rank, n_views, world_size).
 
-    Ranks get floor(n/world) or ceil(n/world) views; every view belongs to exactly one rank.
+    Ranks get floor(n/world) or ceil(n/world) views; every view belongs to exactly one rank.  Interleave when
+    neighbouring views cost alike (an orbit of cameras: views near the poles of a UV sphere rasterize slivers):
+    a step takes as long as the slowest rank, and on c4 over 8 GPUs the contiguous shares differ by 13 %
+    (0.66 .. 0.75 ms), the interleaved ones by 0.6 % (profiles/tools/slice_times.py).
     """
     if world_size is None:
         world_size = dist.get_world_size() if dist.is_initialized() else 1
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
+    if interleaved:
+        return range(int(rank), int(n_views), int(world_size))
     base, extra = divmod(int(n_views), int(world_size))
     start = rank * base + min(rank, extra)
     return range(start, start + base + (1 if rank < extra else 0))

@@ -74,3 +74,7 @@ def test_shard_views_partitions():
             parts = [list(shard_views(n, r, world)) for r in range(world)]
             assert sum(parts, []) == list(range(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
+            dealt = [list(shard_views(n, r, world, interleaved=True)) for r in range(world)]
+            assert sorted(sum(dealt, [])) == list(range(n))                      # a partition as well
+            assert max(map(len, dealt)) - min(map(len, dealt)) <= 1
+            assert all(v % world == r for r, part in enumerate(dealt) for v in part)
