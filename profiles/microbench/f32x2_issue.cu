@@ -1,3 +1,4 @@
+// Build on the GPU box: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o f32x2_issue f32x2_issue.cu
 // Micro-benchmark: issue cost of packed fp32 (mul/add .f32x2, sm_100+) against scalar FMUL/FADD.
 #include <cstdio>
 #include <cuda_runtime.h>

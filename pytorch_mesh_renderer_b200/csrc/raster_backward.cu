@@ -196,15 +196,18 @@ __device__ __forceinline__ void red_add_if(bool ok, float *addr, float v) {
 // walks it block by block, one lane per pixel.  The three per-pixel inputs of a block -- ids [4][8],
 // barycentrics [4][8][3], gradient rows [4][8][A] -- are boxes of 2-D tensor maps over [B*H][W*c] and
 // arrive in shared memory by TMA (cp.async.bulk.tensor.2d, one elected lane, completion on a per-warp
-// mbarrier; SASS UTMALDG): the box of the NEXT block is requested as soon as the lanes have read the
-// current one, so it lands while the current block is processed, no registers are held for it and the SM
-// issues no address arithmetic, LDG or STS for it.  Everything that depends on the lane only (its role in
-// the reduction, shared-memory addresses, barrier) is set up once per strip.
+// mbarrier; SASS UTMALDG): the boxes of the NEXT block are requested once the values of the current one
+// have been used (after the row stores), so they land during the reduction, no registers are held for them
+// and the SM issues no address arithmetic, LDG or STS for them.  What depends on the lane only (its role in
+// the reduction, shared-memory addresses, barrier) is re-derived per block from an opaque copy of the
+// thread index (kept in registers across the loop it would be spilled).
 //
-// Per block, every covered lane evaluates its per-pixel sums -- per corner k the three vertex terms and
-// the A products (g_a*alpha)*b_k, E = 3 + A columns per corner -- and parks them as ONE row of float4
-// slots in shared memory.  Lanes are grouped by triangle id with match.any and the rows of one triangle
-// are made consecutive (warp scan over the group sizes); a group is cut into PIECES of at most
+// Per block: coverage and triangle id of every pixel in raster order; the pixels are then SORTED by triangle
+// inside the warp (match.any + one warp scan give every pixel its row; lane L takes over the pixel whose row
+// is L) so that the rows of one triangle are consecutive and a lane's row is its lane index.  Every covered
+// lane evaluates its per-pixel sums -- per corner k the three vertex terms and the A products (g_a*alpha)*b_k,
+// E = 3 + A columns per corner -- and parks them as ONE row of float4 slots in shared memory (conflict-free:
+// a quarter warp writes eight consecutive rows); a triangle's rows are cut into PIECES of at most
 // kPieceRows rows.  The reduction runs SLOTS pieces side by side: U = ceil(E/4) lanes per corner,
 // J = 3U lanes per piece, lane (corner, u) owning the four columns e = u, u+U, u+2U, u+3U of its corner,
 // which the row layout keeps in one float4 -- one 128-bit shared load and four adds per (piece, row) for
