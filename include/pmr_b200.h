@@ -89,7 +89,7 @@ PMR_API int pmr_set_small_mesh_threshold(pmr_context *ctx, int triangles);
  */
 #define PMR_STAGE_BIN 0      /* clearing the depth keys and the large-triangle counters */
 #define PMR_STAGE_RASTER 1   /* raster_tile_kernel (big triangles; whole pass for tiny meshes) */
-#define PMR_STAGE_BACKWARD 2 /* backward kernels (atomic: one kernel; ordered: boxes + gather) */
+#define PMR_STAGE_BACKWARD 2 /* backward kernels (atomic: one kernel; ordered: radix sort by vertex + in-order fold) */
 #define PMR_STAGE_INTERP 3   /* standalone interpolate_kernel */
 #define PMR_STAGE_SCATTER 4  /* scatter_small_kernel (small triangles -> depth keys; lists the large ones) */
 #define PMR_STAGE_RESOLVE 5  /* resolve_kernel (depth keys -> ids / bary / z / interpolated image) */
