@@ -37,7 +37,7 @@ struct Context {
   int sm_count = 148;
   long long peer_wait_cycles = 19000000000ll;   // reduce_partials_kernel gives up after this many SM cycles (~10 s)
   int no_tma = 0;                      // PMR_NO_TMA: per-pixel loads instead of tensor-map boxes (tests of that path)
-  int strip_blocks_override = 0;       // PMR_STRIP_BLOCKS: 8x4 blocks per warp of the backward kernel (0 = automatic)
+  int strip_blocks_override = 0;       // PMR_STRIP_BLOCKS: 8x4 blocks per warp of the backward (and, up to 4, resolve) kernel (0 = automatic)
   int small_mesh_threshold = 64;      // T at or below this: the tile kernel alone, every tile walks all triangles
   Buffer bins, scratch, keys, centers, staging;   // staging: device copies of the host entry point's buffers
   int centers_w = -1, centers_h = -1;  // image size the pixel-centre table was built for

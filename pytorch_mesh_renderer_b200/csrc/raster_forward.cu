@@ -1167,6 +1167,7 @@ int forward_impl(Context *ctx, const float *verts, const int32_t *tris, int B, i
     int strip = kResolveStrip;
     const long long cta_rows = (long long)((H + 2 * kResolveWarps - 1) / (2 * kResolveWarps)) * B;
     while (strip > 1 && cta_rows * ((W + 16 * strip - 1) / (16 * strip)) < 12LL * 6 * ctx->sm_count) strip >>= 1;
+    if (ctx->strip_blocks_override > 0) strip = min(kResolveStrip, ctx->strip_blocks_override);   // tests of the strip loop
     dim3 grid((W + 16 * strip - 1) / (16 * strip), (H + 2 * kResolveWarps - 1) / (2 * kResolveWarps), B);
     // the staged outputs as tensor maps (PMR_NO_TMA=1 or an array the copy engine cannot describe: per-row copies)
     OutputMaps maps;

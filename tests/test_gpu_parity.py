@@ -405,8 +405,23 @@ def test_random_scenes_vs_oracle(pmr, oracle, threshold, seed):
     sub-pixel to screen-filling, shared vertices, mixed-sign and tiny w, degenerate and duplicated triangles,
     attribute counts with and without a specialised kernel -- everything bit-exact against the oracle
     (forward buffers, image, ORDERED gradients), ATOMIC gradients within the summation-order bound."""
+    _check_random_scene(pmr, oracle, seed)
+
+
+# Sizes that the tensor-map paths take with partly filled boxes: W a multiple of 4 but not of 8 (half a block at the
+# right edge, clipped by the copy engine), strips that end inside the image, H a multiple of 4 or not (tensor stores
+# of the resolve kernel or per-row copies), a single block row.
+@pytest.mark.parametrize("size", [(36, 20), (100, 52), (12, 8), (44, 64), (68, 36), (20, 4), (132, 16), (260, 30)],
+                         ids=lambda s: "%dx%d" % s)
+def test_random_scenes_partial_boxes(pmr, oracle, size):
+    _check_random_scene(pmr, oracle, 500 + size[0], size)
+
+
+def _check_random_scene(pmr, oracle, seed, size=None):
     rng = np.random.default_rng(1000 + seed)
     W, H = int(rng.choice([1, 7, 16, 33, 64, 97, 130])), int(rng.choice([1, 5, 16, 31, 64, 75, 128]))
+    if size is not None:
+        W, H = size
     B = int(rng.integers(1, 4))
     A = int(rng.choice([1, 3, 4, 7, 9, 12, 13]))
     kind = seed % 3
