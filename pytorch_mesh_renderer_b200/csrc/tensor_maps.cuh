@@ -18,6 +18,12 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Box at element (c0, row c1) of the mapped array to shared memory at `dst` (128-byte aligned); completion is counted
+// in bytes on the mbarrier at `bar` (the caller has announced them with arrive.expect_tx); the part of a box outside
+// the array arrives as zeros.  REFILLING a box: the copy engine writes through the async proxy and is ordered with
+// this warp's shared-memory LOADS of the previous contents by nothing -- not by program order, not by __syncwarp
+// (which ptxas drops in converged code).  Issue the refill only after an instruction has consumed what was loaded
+// (then the loads have returned), as backward_blocks_kernel does after its row stores.
 __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
@@ -60,15 +66,11 @@ static inline bool make_block_map(CUtensorMap *map, CUtensorMapDataType type, co
 
 // Box of the shared-memory array at `src` (dense [4][box_inner], 128-byte aligned) to the array at element
 // (c0, row c1); elements outside the array are not written.  The issuing lane commits and waits for the reads
-// (tma_store_wait_read) before the shared memory is rewritten or the CTA exits.
+// (cp.async.bulk.commit_group + wait_group.read 0) before the shared memory is rewritten or the CTA exits, and
+// the writers of the shared memory execute fence.proxy.async.shared::cta before the store is issued.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, unsigned src) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
                ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
-}
-
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 }  // namespace pmr
