@@ -237,8 +237,12 @@ __device__ __forceinline__ void block_epilogue(float *stage, int b, int blk_x0, 
   if (maps != nullptr && vec_ok && rows == 4 && (out_image == nullptr || staged)) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy reads
     __syncwarp();
-    // defer_wait: the caller (lane 0) waits for the reads before the stage is written again or the warp exits
-    if (lane == 0) {
+    // defer_wait: the caller waits for the reads before the stage is written again or the warp exits -- on the
+    // lane elect.sync picks, which is the same lane every time for the same (full) mask.  (elect.sync rather than
+    // `lane == 0`: the copy instructions take their operands from uniform registers, and only behind an election
+    // does the compiler know that one lane issues them; otherwise it loops over the "active lanes" -- 11
+    // instructions per copy.)
+    if (elect_one()) {
       const unsigned stage_at = (unsigned)__cvta_generic_to_shared(stage);
       tma_store_2d(&maps->bary, 3 * blk_x0, b * H + blk_y0, stage_at);
       if (out_image != nullptr) tma_store_2d(&maps->image, A * blk_x0, b * H + blk_y0, stage_at + 4u * (unsigned)kImageAt);
@@ -951,7 +955,7 @@ resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma, int strip_b
   const int iy = y0 + (lane >> 3);
   const unsigned bar = (unsigned)__cvta_generic_to_shared(&ready_all[warp]);
   if (use_tma) {
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(256 * strip_blocks)) : "memory");
@@ -1000,7 +1004,7 @@ resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma, int strip_b
     // (Gathering the 3*A corner attributes here, together with the vertices, was measured: 60 registers
     // instead of 38 cost more occupancy than the shorter dependency chain gained: 0.355 -> 0.411 ms.)
     if (use_tma && it > 0) {               // the previous block's tensor stores have read the stage
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
     }
     block_epilogue<SHADE ? 0 : A_STATIC>(stage_all[warp], b, blk_x0, y0, W, H, V, best, tris, attrs, background, A,
@@ -1029,7 +1033,7 @@ resolve_kernel(const __grid_constant__ OutputMaps maps, int use_tma, int strip_b
     }
     if (!use_tma) __syncwarp();            // the stage is rewritten by the next block
   }
-  if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (use_tma && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // Standalone interpolation (rast.py:118-150) from existing id / barycentric buffers.
